@@ -1,0 +1,152 @@
+/*
+ * tdb200.h — C ABI of libtdb200.so: the B200 (sm_100a) implementation of TurboDiffusion's denoise hot path.
+ *
+ * This is the drop-in boundary.  Every entry point replaces one interface of the reference
+ * (thu-ml/TurboDiffusion; citations are file:line inside that repository):
+ *
+ *   turbo_diffusion_ops.quant_cuda        turbodiffusion/ops/quant/quant.cu:28-71     -> tdb200_quant_int8_block128
+ *   turbo_diffusion_ops.gemm_cuda         turbodiffusion/ops/gemm/gemm.cu:27-68       -> tdb200_gemm_w8a8
+ *   turbo_diffusion_ops.rms_norm_cuda     turbodiffusion/ops/norm/rmsnorm.cu:57-59    -> tdb200_rms_norm_f32
+ *   turbo_diffusion_ops.layer_norm_cuda   turbodiffusion/ops/norm/layernorm.cu:60-62  -> tdb200_layer_norm_f32
+ *   ops.FastRMSNorm / FastLayerNorm fwd   turbodiffusion/ops/core.py:441-442,477-478  -> tdb200_rms_norm / tdb200_layer_norm
+ *   AdaLN modulate / gate (caller math)   turbodiffusion/rcm/networks/wan2pt1.py:398-417 -> tdb200_layer_norm_modulate[_quant], tdb200_gate_residual
+ *   rope_apply                            turbodiffusion/rcm/networks/wan2pt1.py:156-178 -> tdb200_rope_interleaved, tdb200_rms_norm_rope
+ *   SLA.utils.get_block_map               turbodiffusion/SLA/utils.py:55-67           -> tdb200_sla_block_map
+ *   spas_sage_attn get_vanilla_qk_quant   call site turbodiffusion/SLA/core.py:200-203 -> tdb200_sla_quant_qk
+ *   Sage block-sparse attention + linear  turbodiffusion/SLA/core.py:231-253          -> tdb200_sla_linear_moments, tdb200_sla_attn_fwd
+ *
+ * Conventions
+ *   - plain pointers and sizes; all pointers are DEVICE pointers unless stated; no allocation inside;
+ *   - every call enqueues work on `stream` (a cudaStream_t passed as void*) and returns without synchronising;
+ *   - return value: TDB200_OK or a negative TDB200_ERR_* code; the library never calls exit();
+ *     tdb200_last_error() returns a thread-local description of the last failure;
+ *   - reentrant per stream; no internal threads, no global mutable state besides per-device caches;
+ *   - 16-bit floating tensors are described by a TDB200_DTYPE_* tag.
+ */
+#ifndef TDB200_H_
+#define TDB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TDB200_ABI_VERSION 1
+
+#define TDB200_OK 0
+#define TDB200_ERR_INVALID_ARG (-1)  /* null pointer, bad size, misaligned buffer            */
+#define TDB200_ERR_UNSUPPORTED (-2)  /* shape/dtype outside what the kernels implement        */
+#define TDB200_ERR_CUDA (-3)         /* a CUDA runtime/driver call failed (see last_error)    */
+#define TDB200_ERR_ARCH (-4)         /* current device is not compute capability 10.x         */
+#define TDB200_ERR_WORKSPACE (-5)    /* caller-provided workspace too small                   */
+
+#define TDB200_DTYPE_BF16 0
+#define TDB200_DTYPE_FP16 1
+
+/* ABI version of the loaded library (== TDB200_ABI_VERSION it was built with). */
+int tdb200_abi_version(void);
+/* Thread-local, NUL-terminated description of the most recent error on this thread ("" if none). */
+const char* tdb200_last_error(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * a1. per-128x128-block symmetric INT8 quantisation   (ops/quant/quant.hpp:86-99,122-164)
+ *   x [m,k] row-major contiguous 16-bit float; q [m,k] int8; s [ceil(m/128), ceil(k/128)] fp32 row-major.
+ *   per block: amax = max(1e-8, max|x|); s = amax/128; q = sat_s8(rint(x * (128/amax))).
+ *   k must be a multiple of 8.  x and q 16-byte aligned.
+ * ------------------------------------------------------------------------------------------- */
+int tdb200_quant_int8_block128(const void* x, int x_dtype, int64_t m, int64_t k, int8_t* q, float* s, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a2. W8A8 GEMM with per-128-K-block rescale   (ops/gemm/kernel.hpp:391-427, utils.hpp:116-121)
+ *   c[i,j] = T( sum_kb float(sum_{t in kb} a_q[i,t]*b_q[j,t]) * (a_s[i/128,kb]*b_s[j/128,kb]) )   fp32 FMA, kb ascending
+ *   then, if bias != NULL,  c[i,j] = T(float(c[i,j]) + float(bias[j]))      (ops/core.py:410-411)
+ *   a_q [m,k] int8, a_s [ceil(m/128), k/128]; b_q [n,k] int8 ("TN": both K-major), b_s [ceil(n/128), k/128];
+ *   bias [n] of dtype c_dtype or NULL; c [m,n] row-major of dtype c_dtype.
+ *   Requires k % 128 == 0 and n % 8 == 0 (the reference silently skips such shapes, gemm/launch.hpp:34-35;
+ *   here they return TDB200_ERR_UNSUPPORTED).  tcgen05 kind::i8, TMA-staged tiles, accumulators in TMEM.
+ * ------------------------------------------------------------------------------------------- */
+int tdb200_gemm_w8a8(const int8_t* a_q, const float* a_s, const int8_t* b_q, const float* b_s, const void* bias,
+                     void* c, int c_dtype, int64_t m, int64_t n, int64_t k, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a3/a4. FastNorm
+ *   *_f32 : the registered-but-unused reference entry points (fp32 in, fp32 out), 1 CTA per row.
+ *   16-bit variants: the whole FastRMSNorm.forward / FastLayerNorm.forward including the caller-side
+ *   casts (x.float() in, .to(x.dtype) out) in ONE pass: y = T(float(x) * rstd * w), etc.
+ *   w / b are fp32 [n] or NULL (no affine).  n % 8 == 0 (16-bit) / n % 4 == 0 (fp32), n <= 16384.
+ * ------------------------------------------------------------------------------------------- */
+int tdb200_rms_norm_f32(const float* x, const float* w, float* y, int64_t m, int64_t n, float eps, void* stream);
+int tdb200_layer_norm_f32(const float* x, const float* w, const float* b, float* y, int64_t m, int64_t n, float eps,
+                          void* stream);
+int tdb200_rms_norm(const void* x, int dtype, const float* w, void* y, int64_t m, int64_t n, float eps, void* stream);
+int tdb200_layer_norm(const void* x, int dtype, const float* w, const float* b, void* y, int64_t m, int64_t n,
+                      float eps, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a5. AdaLN prologue / epilogue   (rcm/networks/wan2pt1.py:398-417)
+ *   layer_norm_modulate:        y = T( float(T(LN(x))) * (1 + scale[j]) + shift[j] )
+ *   layer_norm_modulate_quant:  same value, emitted directly as a1-format int8 + block scales
+ *                               (one stats pass + one tile pass instead of LN, 2 casts, modulate, quant).
+ *                               row_stats: workspace of 2*m floats (mean, rstd per row).
+ *   gate_residual:              out = T( x + T( y * T(gate[j]) ) )          (x + y*e under bf16 tensors)
+ *   scale/shift/gate: fp32 [n] (one modulation vector: batch 1 per call).
+ * ------------------------------------------------------------------------------------------- */
+int tdb200_layer_norm_modulate(const void* x, int dtype, const float* scale, const float* shift, void* y, int64_t m,
+                               int64_t n, float eps, void* stream);
+int tdb200_layer_norm_modulate_quant(const void* x, int dtype, const float* scale, const float* shift, int8_t* q,
+                                     float* s, float* row_stats, int64_t m, int64_t n, float eps, void* stream);
+int tdb200_gate_residual(const void* x, const void* y, const float* gate, void* out, int dtype, int64_t m, int64_t n,
+                         void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a6. RoPE, interleaved pairs   (rcm/networks/wan2pt1.py:156-178; flash_attn interleaved=True)
+ *   x, y [l, h, d] contiguous 16-bit; angles [l, d/2] fp32 (radians).
+ *   y[2i] = T(x[2i]*cos - x[2i+1]*sin), y[2i+1] = T(x[2i]*sin + x[2i+1]*cos), math in fp32.
+ *   rms_norm_rope: y = rope( T( rmsnorm_{over h*d}(x) * w ) ) in one pass (norm_q/norm_k + rope_apply).
+ * ------------------------------------------------------------------------------------------- */
+int tdb200_rope_interleaved(const void* x, int dtype, const float* angles, void* y, int64_t l, int64_t h, int64_t d,
+                            void* stream);
+int tdb200_rms_norm_rope(const void* x, int dtype, const float* w, const float* angles, void* y, int64_t l, int64_t h,
+                         int64_t d, float eps, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a7-a10. SLA / SageSLA.  q, k, v, out are [b, l, h, d] contiguous 16-bit (the layout the module is
+ * called with, SLA/core.py:181-183), d in {64, 128}.  Block sizes: BLKQ = 128 query rows, BLKK = 64 key rows
+ * (the non-sm90 branch, SLA/core.py:191-193).  mblk = ceil(l/128), nblk = ceil(l/64).
+ *
+ * tdb200_sla_quant_qk   one pass over q and two over k:
+ *     kmean  [b,h,d]  fp32   = sum_l k / l  (T-rounded copy is what is subtracted, SLA/utils.py:56)
+ *     q_i8   [b,h,l,d] int8, q_scale [b,h,mblk];  k_i8 [b,h,l,d] int8 of T(k - T(kmean)), k_scale [b,h,nblk]
+ *                             scale = amax/127 + 1e-7, round half away from zero (SpargeAttn get_vanilla_qk_quant)
+ *     q_pool [b,h,mblk,d] T,  k_pool [b,h,nblk,d] T   block means (SLA/utils.py:21-52; actual row count in the tail)
+ * tdb200_sla_block_map  pooled score T(q_pool . k_pool^T), top-`topk` per row (ties -> lowest index),
+ *     sparse_map [b,h,mblk,nblk] int8 0/1 (SLA/utils.py:64-66) and lut [b,h,mblk,topk] int32 ascending block ids.
+ * tdb200_sla_linear_moments   phi = softmax over d;  kv [b,h,d(v),d(k)] fp32 = sum_l v[l,:]^T phi(k)[l,:],
+ *     ksum [b,h,d] fp32 = sum_l phi(k)[l,:]   (SLA/core.py:243-247).  Both must be zeroed by the caller
+ *     (they are accumulated, so sequence shards can be summed with one all-reduce).
+ * tdb200_sla_attn_fwd   o = T( sparse_softmax_attention(q_i8,k_i8,v; lut) + proj( phi(q) kv / (1e-5 + phi(q).ksum) ) )
+ *     kvw [b,h,d(out),d(k)] T = (proj_w . kv) so that proj is folded into the moment matrix; proj_b [d] fp32.
+ *     The int8 QK^T, online softmax (exp2), PV, linear branch and merge run in one tcgen05 kernel.
+ * ------------------------------------------------------------------------------------------- */
+int tdb200_sla_quant_qk(const void* q, const void* k, int dtype, int64_t b, int64_t l, int64_t h, int64_t d,
+                        float* kmean, int8_t* q_i8, float* q_scale, int8_t* k_i8, float* k_scale, void* q_pool,
+                        void* k_pool, void* stream);
+int tdb200_sla_block_map(const void* q_pool, const void* k_pool, int dtype, int64_t b, int64_t h, int64_t mblk,
+                         int64_t nblk, int64_t d, int64_t topk, int8_t* sparse_map, int32_t* lut, void* stream);
+int tdb200_sla_linear_moments(const void* k, const void* v, int dtype, int64_t b, int64_t l, int64_t h, int64_t d,
+                              float* kv, float* ksum, void* stream);
+int tdb200_sla_attn_fwd(const int8_t* q_i8, const float* q_scale, const int8_t* k_i8, const float* k_scale,
+                        const void* v, const void* q, int dtype, const int32_t* lut, int64_t topk, const void* kvw,
+                        const float* ksum, const float* proj_b, void* out, int64_t b, int64_t l, int64_t lk,
+                        int64_t h, int64_t d, float sm_scale, void* stream);
+
+/* Diagnostics: runs a 128x128x64 bf16 tcgen05 MMA with a K-major A and an MN-major B tile staged by TMA and
+ * writes the fp32 product to d_out [128,128].  a [128,64] bf16 row-major, b [64,128] bf16 row-major (d = a.b). */
+int tdb200_selftest_umma_bf16(const void* a, const void* b, float* d_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TDB200_H_ */

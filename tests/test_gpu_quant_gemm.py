@@ -1,0 +1,129 @@
+"""GPU parity: a1 int8 block quant and a2 W8A8 tcgen05 GEMM against the CPU oracle (bit-exact)."""
+import pytest
+import torch
+
+from oracle import td_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk(m, k, seed, dtype=torch.bfloat16, outliers=True):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(m, k, generator=g)
+    if outliers and k >= 16:
+        x[:, :: max(1, k // 7)] *= 20.0  # outlier channels exercise the per-block scales
+    return x.to(dtype)
+
+
+@pytest.mark.parametrize("m,k", [(128, 128), (256, 1536), (120, 256), (1, 128), (333, 640), (513, 136), (7, 8)])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_quant_bit_exact(cuda, m, k, dtype):
+    import turbodiffusion_b200.ops as ops
+    x = _mk(m, k, 1000 + m + k, dtype)
+    q_ref, s_ref = O.int8_quant(x)
+    q, s = ops.int8_quant(x.to(cuda))
+    torch.cuda.synchronize()
+    assert torch.equal(s.cpu(), s_ref), "block scales must be bit-identical"
+    assert torch.equal(q.cpu(), q_ref), f"int8 codes differ at {(q.cpu() != q_ref).sum().item()} positions"
+
+
+def test_quant_zero_block_and_preallocated_outputs(cuda):
+    from turbodiffusion_b200.turbo_diffusion_ops import quant_cuda
+    x = torch.zeros(256, 256, dtype=torch.bfloat16)
+    x[130:, 128:] = _mk(126, 128, 5)
+    q_ref, s_ref = O.int8_quant(x)
+    q = torch.full((256, 256), 77, dtype=torch.int8, device=cuda)
+    s = torch.full((2, 2), -1.0, device=cuda)
+    q2, s2 = quant_cuda(x.to(cuda), q, s)
+    assert q2.data_ptr() == q.data_ptr() and s2.data_ptr() == s.data_ptr()
+    assert torch.equal(q.cpu(), q_ref) and torch.equal(s.cpu(), s_ref)
+    assert s_ref[0, 0].item() == pytest.approx(1e-8 / 128)  # amax clamp of an all-zero block
+
+
+def test_quant_rejects_fp32(cuda):
+    from turbodiffusion_b200.turbo_diffusion_ops import quant_cuda
+    with pytest.raises(RuntimeError):
+        quant_cuda(torch.zeros(128, 128, device=cuda))
+
+
+GEMM_SHAPES = [
+    (128, 256, 128),     # one tile, one K-block
+    (128, 256, 512),     # K pipeline wraps the 4-stage ring
+    (256, 512, 1536),    # several tiles
+    (120, 256, 256),     # ragged M (Wan tail: 32760 % 128 = 120)
+    (300, 384, 640),     # ragged M, N not a multiple of the 256 tile
+    (129, 136, 128),     # N % 128 != 0 (n % 8 == 0)
+    (1, 128, 128),
+    (2048, 1536, 1536),  # more tiles than SMs would need at 148 CTAs: exercises the persistent loop
+]
+
+
+@pytest.mark.parametrize("m,n,k", GEMM_SHAPES)
+def test_gemm_bit_exact_vs_oracle(cuda, m, n, k):
+    from turbodiffusion_b200.turbo_diffusion_ops import gemm_cuda
+    x = _mk(m, k, 11 * m + k)
+    w = _mk(n, k, 13 * n + k, outliers=False) * 0.05
+    a_q, a_s = O.int8_quant(x)
+    b_q, b_s = O.int8_quant(w.to(torch.bfloat16))
+    ref = O.int8_gemm(a_q, a_s, b_q, b_s, torch.bfloat16)
+    c = torch.full((m, n), float("nan"), dtype=torch.bfloat16, device=cuda)
+    gemm_cuda(a_q.to(cuda), a_s.to(cuda), b_q.to(cuda), b_s.to(cuda), c)
+    torch.cuda.synchronize()
+    got = c.cpu()
+    assert not torch.isnan(got.float()).any(), "some outputs were never written"
+    neq = (got.view(torch.int16) != ref.view(torch.int16))
+    assert not neq.any(), (f"{neq.sum().item()} / {neq.numel()} outputs differ; max abs "
+                           f"{(got.float() - ref.float()).abs().max().item():.4g}; first rows {neq.nonzero()[:5].tolist()}")
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_int8_linear_with_bias_matches_module_semantics(cuda, dtype):
+    import turbodiffusion_b200.ops as ops
+    m, n, k = 200, 384, 256
+    x = _mk(m, k, 3, dtype)
+    w = (_mk(n, k, 4, dtype, outliers=False).float() * 0.05).to(dtype)
+    bias = _mk(1, n, 5, dtype, outliers=False)[0]
+    w_q, w_s = O.int8_quant(w)
+    ref = O.int8_linear(x, w_q, w_s, bias)
+    lin = ops.Int8Linear(k, n, bias=True, dtype=dtype).to(cuda)
+    lin.int8_weight.copy_(w_q)
+    lin.scale.copy_(w_s)
+    lin.bias.copy_(bias)
+    got = lin(x.to(cuda).reshape(2, 100, k)).reshape(m, n).cpu()
+    assert torch.equal(got.view(torch.int16), ref.view(torch.int16))
+    assert sorted(lin.state_dict().keys()) == ["bias", "int8_weight", "scale"]
+
+
+def test_gemm_unsupported_k_raises(cuda):
+    from turbodiffusion_b200.turbo_diffusion_ops import gemm_cuda
+    from turbodiffusion_b200._lib import Tdb200Error
+    a = torch.zeros(128, 100, dtype=torch.int8, device=cuda)
+    s = torch.ones(1, 1, device=cuda)
+    c = torch.zeros(128, 128, dtype=torch.bfloat16, device=cuda)
+    with pytest.raises(Tdb200Error):
+        gemm_cuda(a, s, a, s, c)
+
+
+def test_gemm_linearity_at_full_wan_shape(cuda):
+    """Size-independent property at the BASELINE shape (M=32760, Wan-1.3B q-projection): with unit scales the GEMM is
+    an exact integer matmul, so C(A, B1 + B2) == C(A, B1) + C(A, B2) exactly while sums stay below 2^8 (bf16-exact)."""
+    from turbodiffusion_b200.turbo_diffusion_ops import gemm_cuda
+    m, n, k = 32760, 1536, 1536
+    g = torch.Generator(device="cuda").manual_seed(0)
+    a = torch.randint(-1, 2, (m, k), generator=g, device=cuda, dtype=torch.int8)
+    # sparse +-1 weights keep |dot| small enough to be exactly representable in bf16
+    b1 = (torch.rand(n, k, generator=g, device=cuda) < 0.01).to(torch.int8)
+    b2 = -(torch.rand(n, k, generator=g, device=cuda) < 0.01).to(torch.int8)
+    ones_a = torch.ones((m + 127) // 128, k // 128, device=cuda)
+    ones_b = torch.ones(n // 128, k // 128, device=cuda)
+    outs = []
+    for b in (b1, b2, b1 + b2):
+        c = torch.empty(m, n, dtype=torch.bfloat16, device=cuda)
+        gemm_cuda(a, ones_a, b.contiguous(), ones_b, c)
+        outs.append(c.float())
+    assert outs[0].abs().max() < 128
+    assert torch.equal(outs[0] + outs[1], outs[2])
+    # spot-check 64 random rows against an exact integer matmul
+    rows = torch.randint(0, m, (64,), device=cuda)
+    ref = (a[rows].float() @ (b1 + b2).float().t())
+    assert torch.equal(outs[2][rows], ref)

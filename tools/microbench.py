@@ -1,0 +1,122 @@
+"""Per-kernel timings on the GPU (CUDA events, L2 flushed between iterations).  Writes gpurun_out/microbench.jsonl.
+
+    python tools/microbench.py [--filter gemm] [--iters 20]
+"""
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import turbodiffusion_b200.ops as ops  # noqa: E402
+from turbodiffusion_b200 import turbo_diffusion_ops as tdo  # noqa: E402
+
+PEAKS = {"hbm_gbs": 6564.5, "bf16_tflops": 1736.7}
+try:
+    PEAKS.update(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))))
+except Exception:
+    pass
+
+dev = torch.device("cuda:0")
+_flush = None
+
+
+def flush_l2():
+    global _flush
+    if _flush is None:
+        _flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    _flush.zero_()
+
+
+def timeit(fn, iters, warmup=3):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    times = []
+    for _ in range(iters):
+        flush_l2()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        fn()
+        e.record()
+        torch.cuda.synchronize()
+        times.append(s.elapsed_time(e))
+    times.sort()
+    return times[len(times) // 2], times[0]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--filter", default="")
+    ap.add_argument("--iters", type=int, default=15)
+    ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "microbench.jsonl"))
+    args = ap.parse_args()
+    os.makedirs(os.path.dirname(args.out), exist_ok=True)
+    results = []
+
+    def record(name, ms_med, ms_min, flops=None, bytes_=None, **extra):
+        r = {"name": name, "ms_median": round(ms_med, 4), "ms_min": round(ms_min, 4)}
+        if flops:
+            r["tflops"] = round(flops / ms_med / 1e9, 1)
+            r["frac_bf16_peak"] = round(flops / ms_med / 1e9 / PEAKS["bf16_tflops"], 3)
+        if bytes_:
+            r["gbs"] = round(bytes_ / ms_med / 1e6, 1)
+            r["frac_hbm_peak"] = round(bytes_ / ms_med / 1e6 / PEAKS["hbm_gbs"], 3)
+        r.update(extra)
+        results.append(r)
+        print(json.dumps(r), flush=True)
+
+    shapes = {"A": (32760, 1536, 8960), "B": (75600, 5120, 13824)}
+    for tag, (L, dim, ffn) in shapes.items():
+        gemms = [("qkv_fused", L, 3 * dim, dim), ("o_proj", L, dim, dim), ("ffn_up", L, ffn, dim), ("ffn_down", L, dim, ffn)]
+        for name, m, n, k in gemms:
+            full = f"gemm_w8a8/{tag}/{name}/{m}x{n}x{k}"
+            if args.filter not in full:
+                continue
+            a = torch.randint(-128, 128, (m, k), device=dev, dtype=torch.int8)
+            b = torch.randint(-128, 128, (n, k), device=dev, dtype=torch.int8)
+            a_s = torch.rand((m + 127) // 128, k // 128, device=dev) * 0.01
+            b_s = torch.rand((n + 127) // 128, k // 128, device=dev) * 0.01
+            c = torch.empty(m, n, dtype=torch.bfloat16, device=dev)
+            med, mn = timeit(lambda: tdo.gemm_cuda(a, a_s, b, b_s, c), args.iters)
+            record(full, med, mn, flops=2.0 * m * n * k, bytes_=m * k + n * k + 2 * m * n)
+            del a, b, c
+        for name, k in (("dim", dim), ("ffn", ffn)):
+            full = f"quant_int8/{tag}/{name}/{L}x{k}"
+            if args.filter in full:
+                x = torch.randn(L, k, device=dev, dtype=torch.bfloat16)
+                q = torch.empty(L, k, dtype=torch.int8, device=dev)
+                s = torch.empty((L + 127) // 128, k // 128, device=dev)
+                med, mn = timeit(lambda: tdo.quant_cuda(x, q, s), args.iters)
+                record(full, med, mn, bytes_=3 * L * k)
+                del x, q
+        x = torch.randn(L, dim, device=dev, dtype=torch.bfloat16)
+        w = torch.rand(dim, device=dev) + 0.5
+        sc, sh = torch.randn(dim, device=dev) * 0.1, torch.randn(dim, device=dev) * 0.1
+        rows = [
+            (f"fast_layernorm/{tag}/{L}x{dim}", lambda: ops.fast_layernorm(x, None, None, 1e-6), 4 * L * dim),
+            (f"fast_rmsnorm/{tag}/{L}x{dim}", lambda: ops.fast_rmsnorm(x, w, 1e-6), 4 * L * dim),
+            (f"ln_modulate/{tag}/{L}x{dim}", lambda: ops.layernorm_modulate(x, sc, sh, 1e-6), 4 * L * dim),
+            (f"ln_modulate_quant/{tag}/{L}x{dim}", lambda: ops.layernorm_modulate_quant(x, sc, sh, 1e-6), 3 * L * dim),
+            (f"gate_residual/{tag}/{L}x{dim}", lambda: ops.gate_residual(x, x, sc), 6 * L * dim),
+        ]
+        heads = dim // 128
+        ang = torch.rand(L, 64, device=dev) * 20
+        rows.append((f"rmsnorm_rope/{tag}/{L}x{dim}", lambda: ops.rmsnorm_rope(x, w, ang, 1e-6, heads), 4 * L * dim))
+        for full, fn, nbytes in rows:
+            if args.filter in full:
+                med, mn = timeit(fn, args.iters)
+                record(full, med, mn, bytes_=nbytes)
+        del x
+
+    with open(args.out, "w") as f:
+        for r in results:
+            f.write(json.dumps(r) + "\n")
+
+
+if __name__ == "__main__":
+    main()

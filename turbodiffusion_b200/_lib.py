@@ -1,0 +1,91 @@
+"""ctypes binding of libtdb200.so (the C ABI declared in include/tdb200.h).
+
+The product path has NO fallback: if the library is missing or a call fails, an exception is raised.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int, c_int64, c_void_p
+
+import torch
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG_DIR, "libtdb200.so")
+
+DTYPE_TAG = {torch.bfloat16: 0, torch.float16: 1}
+
+_P, _I64, _F, _I = c_void_p, c_int64, c_float, c_int
+
+# name -> argtypes (restype is int unless listed in _RESTYPES)
+_PROTOS = {
+    "tdb200_abi_version": [],
+    "tdb200_last_error": [],
+    "tdb200_quant_int8_block128": [_P, _I, _I64, _I64, _P, _P, _P],
+    "tdb200_gemm_w8a8": [_P, _P, _P, _P, _P, _P, _I, _I64, _I64, _I64, _P],
+    "tdb200_rms_norm_f32": [_P, _P, _P, _I64, _I64, _F, _P],
+    "tdb200_layer_norm_f32": [_P, _P, _P, _P, _I64, _I64, _F, _P],
+    "tdb200_rms_norm": [_P, _I, _P, _P, _I64, _I64, _F, _P],
+    "tdb200_layer_norm": [_P, _I, _P, _P, _P, _I64, _I64, _F, _P],
+    "tdb200_layer_norm_modulate": [_P, _I, _P, _P, _P, _I64, _I64, _F, _P],
+    "tdb200_layer_norm_modulate_quant": [_P, _I, _P, _P, _P, _P, _P, _I64, _I64, _F, _P],
+    "tdb200_gate_residual": [_P, _P, _P, _P, _I, _I64, _I64, _P],
+    "tdb200_rope_interleaved": [_P, _I, _P, _P, _I64, _I64, _I64, _P],
+    "tdb200_rms_norm_rope": [_P, _I, _P, _P, _P, _I64, _I64, _I64, _F, _P],
+    "tdb200_sla_quant_qk": [_P, _P, _I, _I64, _I64, _I64, _I64, _P, _P, _P, _P, _P, _P, _P, _P],
+    "tdb200_sla_block_map": [_P, _P, _I, _I64, _I64, _I64, _I64, _I64, _I64, _P, _P, _P],
+    "tdb200_sla_linear_moments": [_P, _P, _I, _I64, _I64, _I64, _I64, _P, _P, _P],
+    "tdb200_sla_attn_fwd": [_P, _P, _P, _P, _P, _P, _I, _P, _I64, _P, _P, _P, _P, _I64, _I64, _I64, _I64, _I64, _F,
+                            _P],
+    "tdb200_selftest_umma_bf16": [_P, _P, _P, _P],
+}
+_RESTYPES = {"tdb200_last_error": c_char_p}
+
+_lib = None
+
+
+class Tdb200Error(RuntimeError):
+    pass
+
+
+def exported_names():
+    return list(_PROTOS.keys())
+
+
+def lib() -> ctypes.CDLL:
+    """Load libtdb200.so (once).  Raises if it has not been built: there is no CPU or eager fallback."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise Tdb200Error(
+                f"{LIB_PATH} not found. Build it with `python -m turbodiffusion_b200._build` "
+                "(or __graft_entry__.build()). turbodiffusion_b200 has no fallback path.")
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, argtypes in _PROTOS.items():
+            fn = getattr(handle, name)  # AttributeError if the library does not export a declared symbol
+            fn.argtypes = argtypes
+            fn.restype = _RESTYPES.get(name, c_int)
+        if handle.tdb200_abi_version() != 1:
+            raise Tdb200Error("libtdb200.so ABI version mismatch")
+        _lib = handle
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib().tdb200_last_error()
+        raise Tdb200Error(f"{what} failed (code {rc}): {msg.decode() if msg else ''}")
+
+
+def stream_ptr(device=None) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def require_cuda(*tensors) -> None:
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise Tdb200Error("turbodiffusion_b200 ops take CUDA tensors only (no CPU fallback)")

@@ -1,0 +1,264 @@
+// a2. W8A8 GEMM with per-128-K-block rescale on tcgen05 (reference semantics: turbodiffusion/ops/gemm/kernel.hpp:391-427,
+// utils.hpp:116-121, output cast kernel.hpp:471-477; bias add ops/core.py:410-411).
+//
+//   c[i,j] = T( fma-chain over kb of  float(int32 dot of K-block kb) * (a_s[i/128,kb]*b_s[j/128,kb]) )  [+ bias]
+//
+// Design (one persistent CTA per SM, 128x256 output tile, 128-deep K-blocks):
+//   warp 8   TMA producer: A tile [128 rows x 128 B] and B tile [256 rows x 128 B] per K-block, 128B-swizzled,
+//            4-stage ring, mbarrier complete_tx.
+//   warp 9   MMA issuer (one elected lane): 4 x tcgen05.mma.kind::i8 (M128 N256 K32) per K-block into one of two
+//            TMEM accumulator buffers (2 x 256 columns of int32), accumulate flag reset at every K-block because the
+//            reference rescales per K-block; tcgen05.commit releases the smem stage and publishes the TMEM buffer.
+//   warps 0-7 dequant/epilogue: thread = one output row (TMEM lane) x 128 columns.  Per K-block: tcgen05.ld the
+//            int32 partial sums, cvt to fp32 (exact, |sum| < 2^22) and FMA with the block scale into 128 fp32
+//            registers, hand the TMEM buffer back; after the last K-block: round to T, add bias, 16-byte stores.
+//            The dequant of K-block kb overlaps the MMAs of K-block kb+1 (double-buffered TMEM).
+// Integer accumulation is exact and the fp32 FMA chain runs in ascending kb order, so the result is bit-identical
+// to the reference restatement (oracle.int8_linear) on the same int8 inputs.
+#include "common.cuh"
+#include "host_common.h"
+
+namespace {
+
+using namespace tdb;
+
+constexpr int BM = 128, BN = 256, BK = 128;
+constexpr int kStages = 4;
+constexpr int kEpiWarps = 8;
+constexpr int kTmaWarp = 8, kMmaWarp = 9;
+constexpr int kThreads = 384;  // warps 0-7 dequant/epilogue, 8 TMA, 9 MMA, 10-11 idle (complete the warpgroup)
+constexpr uint32_t kATile = BM * BK;            // 16 KB
+constexpr uint32_t kBTile = BN * BK;            // 32 KB
+constexpr uint32_t kStageBytes = kATile + kBTile;
+constexpr uint32_t kTmemCols = 512;             // 2 accumulator buffers x 256 int32 columns
+constexpr size_t kSmemBytes = 1024 /*align slack*/ + size_t(kStages) * kStageBytes + 256 /*barriers*/;
+
+struct GemmParams {
+  const float* a_s;
+  const float* b_s;
+  const void* bias;
+  void* c;
+  int64_t m, n, k;
+  int k_blocks, n_tiles, total_tiles;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + size_t(kStages) * kStageBytes);
+  uint64_t* full_bar = bars;                      // [kStages]  TMA -> MMA
+  uint64_t* empty_bar = bars + kStages;           // [kStages]  MMA -> TMA
+  uint64_t* tmem_full = bars + 2 * kStages;       // [2]        MMA -> epilogue
+  uint64_t* tmem_empty = bars + 2 * kStages + 2;  // [2]        epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], kEpiWarps);
+    }
+    mbar_fence_init();
+  }
+  if (warp == kMmaWarp) tmem_alloc<kTmemCols>(tmem_slot);
+  if (warp == kTmaWarp && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp >= kEpiWarps) {
+   reg_dealloc<80>();
+   if (warp == kTmaWarp) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int m_tile = tile / p.n_tiles, n_tile = tile % p.n_tiles;
+        for (int kb = 0; kb < p.k_blocks; ++kb, ++it) {
+          const uint32_t stage = it % kStages, phase = (it / kStages) & 1u;
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          uint8_t* sa = smem + size_t(stage) * kStageBytes;
+          mbar_expect_tx(&full_bar[stage], kStageBytes);
+          tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BK, m_tile * BM);
+          tma_load_2d(sa + kATile, &tmap_b, &full_bar[stage], kb * BK, n_tile * BN);
+        }
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(kDFmtS32, kFmtS8, kFmtS8, 0, 0, BM, BN);
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        for (int kb = 0; kb < p.k_blocks; ++kb, ++it) {
+          const uint32_t stage = it % kStages, phase = (it / kStages) & 1u;
+          const uint32_t buf = it & 1u, bphase = (it >> 1) & 1u;
+          mbar_wait(&tmem_empty[buf], bphase ^ 1u);
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after_sync();
+          const uint32_t sa = smem_u32(smem + size_t(stage) * kStageBytes);
+          const uint64_t adesc = make_desc_kmajor_sw128(sa);
+          const uint64_t bdesc = make_desc_kmajor_sw128(sa + kATile);
+          const uint32_t d = tmem_base + buf * BN;
+#pragma unroll
+          for (int ks = 0; ks < BK / 32; ++ks) {
+            // advance 32 bytes (one K=32 int8 slice) inside the 128B swizzle row: +2 in 16-byte units
+            umma_i8_ss(d, adesc + uint64_t(ks * 2), bdesc + uint64_t(ks * 2), idesc, ks > 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          umma_commit(&tmem_full[buf]);
+        }
+      }
+    }
+   }
+  } else {
+    // ------------------------------------------------------------------ dequant + epilogue warps
+    reg_alloc<216>();
+    const int q4 = warp & 3;           // TMEM lane quarter this warp may access
+    const int half = warp >> 2;        // which 128-column half of the 256-wide tile
+    const uint32_t lane_addr = uint32_t(q4 * 32) << 16;
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int m_tile = tile / p.n_tiles, n_tile = tile % p.n_tiles;
+      const int64_t col0 = int64_t(n_tile) * BN + half * 128;
+      const bool half_active = col0 < p.n;
+      const float* as_row = p.a_s + int64_t(m_tile) * p.k_blocks;
+      const float* bs_row = p.b_s + (half_active ? (col0 >> 7) : 0) * p.k_blocks;
+
+      float acc[128];
+#pragma unroll
+      for (int j = 0; j < 128; ++j) acc[j] = 0.0f;
+
+      float scale_next = __ldg(as_row) * __ldg(bs_row);
+      for (int kb = 0; kb < p.k_blocks; ++kb, ++it) {
+        const uint32_t buf = it & 1u, bphase = (it >> 1) & 1u;
+        const float scale = scale_next;
+        if (kb + 1 < p.k_blocks) scale_next = __ldg(as_row + kb + 1) * __ldg(bs_row + kb + 1);
+        mbar_wait(&tmem_full[buf], bphase);
+        tc_fence_after_sync();
+        const uint32_t t0 = tmem_base + lane_addr + buf * BN + half * 128;
+#pragma unroll
+        for (int c = 0; c < 4; c += 2) {
+          uint32_t r0[32], r1[32];
+          tmem_ld_x32(t0 + c * 32, r0);
+          tmem_ld_x32(t0 + c * 32 + 32, r1);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            acc[c * 32 + j] = fmaf(__int2float_rn(static_cast<int>(r0[j])), scale, acc[c * 32 + j]);
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            acc[c * 32 + 32 + j] = fmaf(__int2float_rn(static_cast<int>(r1[j])), scale, acc[c * 32 + 32 + j]);
+        }
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+      }
+
+      // ---- tile epilogue: round to T, (+bias), store this thread's 128 consecutive outputs
+      const int64_t row = int64_t(m_tile) * BM + q4 * 32 + lane;
+      if (row < p.m && half_active) {
+        T* crow = static_cast<T*>(p.c) + row * p.n + col0;
+        const T* bias = static_cast<const T*>(p.bias);
+#pragma unroll
+        for (int ch = 0; ch < 16; ++ch) {
+          if (col0 + ch * 8 < p.n) {  // n % 8 == 0: a chunk is fully in or out
+            uint32_t w[4];
+            if (bias != nullptr) {
+              const uint4 bw4 = *reinterpret_cast<const uint4*>(bias + col0 + ch * 8);
+              const uint32_t bw[4] = {bw4.x, bw4.y, bw4.z, bw4.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float y0 = F16Traits<T>::round(acc[ch * 8 + 2 * j]);
+                const float y1 = F16Traits<T>::round(acc[ch * 8 + 2 * j + 1]);
+                w[j] = F16Traits<T>::pack(y0 + F16Traits<T>::lo(bw[j]), y1 + F16Traits<T>::hi(bw[j]));
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) w[j] = F16Traits<T>::pack(acc[ch * 8 + 2 * j], acc[ch * 8 + 2 * j + 1]);
+            }
+            stg_v4(crow + ch * 8, make_uint4(w[0], w[1], w[2], w[3]));
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == kMmaWarp) {
+    tc_fence_after_sync();
+    tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+
+template <typename T>
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
+  static bool attr_set = false;  // per-process; the attribute is per-function and idempotent
+  if (!attr_set) {
+    if (int rc = check_cuda(cudaFuncSetAttribute(gemm_w8a8_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 static_cast<int>(kSmemBytes)),
+                            "cudaFuncSetAttribute(gemm_w8a8)"))
+      return rc;
+    attr_set = true;
+  }
+  const int grid = p.total_tiles < sm_count() ? p.total_tiles : sm_count();
+  gemm_w8a8_kernel<T><<<grid, kThreads, kSmemBytes, st>>>(ta, tb, p);
+  return check_launch("gemm_w8a8_kernel");
+}
+
+}  // namespace
+
+extern "C" int tdb200_gemm_w8a8(const int8_t* a_q, const float* a_s, const int8_t* b_q, const float* b_s,
+                                const void* bias, void* c, int c_dtype, int64_t m, int64_t n, int64_t k,
+                                void* stream) {
+  using namespace tdb;
+  if (!a_q || !a_s || !b_q || !b_s || !c) return fail(TDB200_ERR_INVALID_ARG, "gemm_w8a8: null pointer");
+  if (m < 0 || n < 0 || k < 0) return fail(TDB200_ERR_INVALID_ARG, "gemm_w8a8: negative size");
+  if (m == 0 || n == 0) return TDB200_OK;
+  if (k == 0 || k % BK != 0)
+    return fail(TDB200_ERR_UNSUPPORTED, "gemm_w8a8: k=%lld must be a positive multiple of 128 (gemm/launch.hpp:181-186)",
+                (long long)k);
+  if (n % 8 != 0) return fail(TDB200_ERR_UNSUPPORTED, "gemm_w8a8: n=%lld must be a multiple of 8", (long long)n);
+  if (!aligned16(a_q) || !aligned16(b_q) || !aligned16(c) || (bias && !aligned16(bias)))
+    return fail(TDB200_ERR_INVALID_ARG, "gemm_w8a8: a_q, b_q, c and bias must be 16-byte aligned");
+  if (m > (int64_t(1) << 31) - 256 || n > (int64_t(1) << 31) - 256 || k > (int64_t(1) << 31) - 256)
+    return fail(TDB200_ERR_UNSUPPORTED, "gemm_w8a8: dimension exceeds int32 TMA coordinates");
+  if (int rc = require_sm100()) return rc;
+
+  CUtensorMap ta, tb;
+  if (int rc = make_tmap_2d(&ta, a_q, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, uint64_t(k), uint64_t(m), uint64_t(k), BK, BM))
+    return rc;
+  if (int rc = make_tmap_2d(&tb, b_q, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, uint64_t(k), uint64_t(n), uint64_t(k), BK, BN))
+    return rc;
+
+  GemmParams p;
+  p.a_s = a_s;
+  p.b_s = b_s;
+  p.bias = bias;
+  p.c = c;
+  p.m = m;
+  p.n = n;
+  p.k = k;
+  p.k_blocks = static_cast<int>(k / BK);
+  p.n_tiles = static_cast<int>(cdiv64(n, BN));
+  const int64_t total = cdiv64(m, BM) * p.n_tiles;
+  if (total > (int64_t(1) << 30)) return fail(TDB200_ERR_UNSUPPORTED, "gemm_w8a8: too many tiles");
+  p.total_tiles = static_cast<int>(total);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (c_dtype == TDB200_DTYPE_BF16) return launch<__nv_bfloat16>(ta, tb, p, st);
+  if (c_dtype == TDB200_DTYPE_FP16) return launch<__half>(ta, tb, p, st);
+  return fail(TDB200_ERR_UNSUPPORTED, "gemm_w8a8: output dtype tag %d (bf16/fp16 only, gemm.cu:41-65)", c_dtype);
+}

@@ -1,0 +1,115 @@
+#include "host_common.h"
+
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <mutex>
+
+namespace tdb {
+
+static thread_local char g_err[512] = {0};
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+const char* last_error_cstr() { return g_err; }
+
+int check_cuda(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return 0;
+  return fail(TDB200_ERR_CUDA, "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+}
+
+int check_launch(const char* kernel_name) { return check_cuda(cudaGetLastError(), kernel_name); }
+
+int sm_count() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
+int require_sm100() {
+  static int ok[64] = {0};  // 0 unknown, 1 ok, -1 bad
+  int dev = 0;
+  int rc = check_cuda(cudaGetDevice(&dev), "cudaGetDevice");
+  if (rc) return rc;
+  if (dev < 0 || dev >= 64) return fail(TDB200_ERR_INVALID_ARG, "device ordinal %d out of range", dev);
+  if (ok[dev] == 0) {
+    int major = 0;
+    rc = check_cuda(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev), "cudaDeviceGetAttribute");
+    if (rc) return rc;
+    ok[dev] = (major == 10) ? 1 : -1;
+  }
+  if (ok[dev] < 0)
+    return fail(TDB200_ERR_ARCH, "libtdb200 kernels are built for sm_100a only; device %d is not compute capability 10.x", dev);
+  return 0;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+static int encode(CUtensorMap* out, CUtensorMapDataType dtype, uint32_t rank, const void* base, const uint64_t* dims,
+                  const uint64_t* strides, const uint32_t* box) {
+  EncodeTiledFn fn = get_encode();
+  if (!fn) return fail(TDB200_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  if (!aligned16(base)) return fail(TDB200_ERR_INVALID_ARG, "TMA base address must be 16-byte aligned");
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(out, dtype, rank, const_cast<void*>(base), reinterpret_cast<const cuuint64_t*>(dims),
+                  reinterpret_cast<const cuuint64_t*>(strides), box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(TDB200_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return 0;
+}
+
+int make_tmap_2d(CUtensorMap* out, const void* base, CUtensorMapDataType dtype, uint32_t elem_bytes, uint64_t inner,
+                 uint64_t outer, uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer) {
+  if (box_inner * elem_bytes > 128 || box_outer > 256)
+    return fail(TDB200_ERR_INVALID_ARG, "TMA box %ux%u exceeds the 128B-swizzle limits", box_inner, box_outer);
+  if (row_stride_bytes % 16 != 0) return fail(TDB200_ERR_INVALID_ARG, "TMA row stride must be a multiple of 16 bytes");
+  uint64_t dims[2] = {inner, outer};
+  uint64_t strides[1] = {row_stride_bytes};
+  uint32_t box[2] = {box_inner, box_outer};
+  return encode(out, dtype, 2, base, dims, strides, box);
+}
+
+int make_tmap_4d(CUtensorMap* out, const void* base, CUtensorMapDataType dtype, uint32_t elem_bytes,
+                 const uint64_t dims[4], const uint64_t strides_bytes[3], const uint32_t box[4]) {
+  if (box[0] * elem_bytes > 128) return fail(TDB200_ERR_INVALID_ARG, "TMA inner box exceeds 128 bytes");
+  for (int i = 0; i < 3; ++i)
+    if (strides_bytes[i] % 16 != 0) return fail(TDB200_ERR_INVALID_ARG, "TMA strides must be multiples of 16 bytes");
+  return encode(out, dtype, 4, base, dims, strides_bytes, box);
+}
+
+}  // namespace tdb
+
+namespace tdb {
+const char* last_error_cstr();
+}
+
+extern "C" int tdb200_abi_version(void) { return TDB200_ABI_VERSION; }
+extern "C" const char* tdb200_last_error(void) { return tdb::last_error_cstr(); }

@@ -1,0 +1,82 @@
+// Diagnostic kernel: one CTA, D[128,128] = A[128,64] . B[64,128] in bf16 with fp32 accumulation on tcgen05.
+// A is staged K-major, B MN-major (rows = K index, N contiguous), both 128B-swizzled by TMA: exactly the operand
+// conventions the SLA attention kernel uses for P (K-major) and V (MN-major).  Used by tests/test_umma_probe.py.
+#include "common.cuh"
+#include "host_common.h"
+
+namespace {
+using namespace tdb;
+
+__global__ void __launch_bounds__(128, 1)
+selftest_umma_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                          float* __restrict__ d_out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;               // 128 rows x 128 B = 16 KB
+  uint8_t* sB = smem + 16384;       // 2 chunks x (64 rows x 128 B) = 16 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 32768);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc<128>(tmem_slot);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(&bars[0], 32768);
+    tma_load_2d(sA, &tmap_a, &bars[0], 0, 0);
+    tma_load_2d(sB, &tmap_b, &bars[0], 0, 0);          // N columns 0..63, K rows 0..63
+    tma_load_2d(sB + 8192, &tmap_b, &bars[0], 64, 0);  // N columns 64..127
+    mbar_wait(&bars[0], 0);
+    tc_fence_after_sync();
+    constexpr uint32_t idesc = make_idesc(kDFmtF32, kFmtBF16, kFmtBF16, 0, 1, 128, 128);
+    const uint64_t adesc = make_desc_kmajor_sw128(smem_u32(sA));
+    const uint64_t bdesc = make_desc_mnmajor_sw128(smem_u32(sB), 8192);
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks)  // K=16 per MMA: A +32 B along its row, B +16 rows (2048 B)
+      umma_f16_ss(tmem_base, adesc + uint64_t(ks * 2), bdesc + uint64_t(ks * 128), idesc, ks > 0 ? 1u : 0u);
+    umma_commit(&bars[1]);
+  }
+  __syncwarp();
+  mbar_wait(&bars[1], 0);
+  tc_fence_after_sync();
+  const int row = warp * 32 + lane;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    uint32_t r[32];
+    tmem_ld_x32(tmem_base + (uint32_t(warp * 32) << 16) + c * 32, r);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) d_out[row * 128 + c * 32 + j] = __uint_as_float(r[j]);
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after_sync();
+    tmem_dealloc<128>(tmem_base);
+  }
+}
+}  // namespace
+
+extern "C" int tdb200_selftest_umma_bf16(const void* a, const void* b, float* d_out, void* stream) {
+  using namespace tdb;
+  if (!a || !b || !d_out) return fail(TDB200_ERR_INVALID_ARG, "selftest_umma_bf16: null pointer");
+  if (int rc = require_sm100()) return rc;
+  CUtensorMap ta, tb;
+  if (int rc = make_tmap_2d(&ta, a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 64, 128, 128, 64, 128)) return rc;
+  if (int rc = make_tmap_2d(&tb, b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 128, 64, 256, 64, 64)) return rc;
+  const size_t smem = 1024 + 32768 + 64;
+  if (int rc = check_cuda(cudaFuncSetAttribute(selftest_umma_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               static_cast<int>(smem)),
+                          "cudaFuncSetAttribute(selftest)"))
+    return rc;
+  selftest_umma_bf16_kernel<<<1, 128, smem, static_cast<cudaStream_t>(stream)>>>(ta, tb, d_out);
+  return check_launch("selftest_umma_bf16_kernel");
+}

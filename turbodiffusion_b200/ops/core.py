@@ -1,0 +1,270 @@
+"""Mirror of the reference operator API `turbodiffusion.ops` (turbodiffusion/ops/core.py), backed by libtdb200.so.
+
+Same function / class names, constructor arguments, buffers and state-dict keys as the reference, so
+`inference/modify_model.py:56-81` (replace_linear_norm) and checkpoints with `int8_weight / scale / bias` keys work
+unchanged.  Additional fused entry points (one HBM pass instead of several) sit below the mirrored ones.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from .._lib import DTYPE_TAG, check, lib, ptr, require_cuda, stream_ptr
+from ..turbo_diffusion_ops import quant_cuda, gemm_cuda, gemm_cuda_swizzle_bias
+
+
+# ------------------------------------------------------------------------------------------------ mirrored API
+def int8_quant(x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """ops/core.py:12-25."""
+    return quant_cuda(x, None, None)
+
+
+def int8_linear(x: torch.Tensor, w_q: torch.Tensor, w_s: torch.Tensor, bias: Optional[torch.Tensor] = None,
+                **kwargs) -> torch.Tensor:
+    """ops/core.py:28-57 (+ optional fused bias: T(T(acc)+bias), the value Int8Linear.forward :408-412 produces)."""
+    assert w_q.dtype == torch.int8, "Weight tensor must be int8."
+    shape = x.shape
+    x = x.reshape(-1, shape[-1])
+    if not x.is_contiguous():
+        x = x.contiguous()
+    m, n = x.shape[0], w_q.shape[0]
+    y = torch.empty(m, n, dtype=x.dtype, device=x.device)  # the reference pre-zeroes (:53); every element is written here
+    x_q, x_s = int8_quant(x)
+    if bias is None:
+        gemm_cuda(x_q, x_s, w_q, w_s, y)
+    else:
+        gemm_cuda_swizzle_bias(x_q, x_s, w_q, w_s, y, bias)
+    return y.reshape(*shape[:-1], n)
+
+
+def int8_linear_prequant(x_q: torch.Tensor, x_s: torch.Tensor, w_q: torch.Tensor, w_s: torch.Tensor,
+                         bias: Optional[torch.Tensor], out_dtype: torch.dtype) -> torch.Tensor:
+    """GEMM on an already-quantised activation (lets q/k/v share one quantisation of the same input)."""
+    y = torch.empty(x_q.shape[0], w_q.shape[0], dtype=out_dtype, device=x_q.device)
+    if bias is None:
+        gemm_cuda(x_q, x_s, w_q, w_s, y)
+    else:
+        gemm_cuda_swizzle_bias(x_q, x_s, w_q, w_s, y, bias)
+    return y
+
+
+def _flatten_rows(x: torch.Tensor):
+    assert x.is_contiguous(), "Input must be contiguous"
+    assert x.dim() in (2, 3), "Input tensors must be batched (3D) or not batched (2D)"
+    return x.reshape(-1, x.shape[-1])
+
+
+def rmsnorm(x: torch.Tensor, w: torch.Tensor, eps: float) -> torch.Tensor:
+    """ops/core.py:139-191: fp32 [M,N] or [B,M,N] in, fp32 out."""
+    require_cuda(x, w)
+    x2 = _flatten_rows(x)
+    if x2.dtype != torch.float32:
+        raise RuntimeError("rmsnorm expects an fp32 input (the module casts with x.float())")
+    y = torch.empty_like(x2)
+    check(lib().tdb200_rms_norm_f32(ptr(x2), ptr(w.float()), ptr(y), x2.shape[0], x2.shape[1], float(eps),
+                                    stream_ptr(x.device)), "rmsnorm")
+    return y.reshape(x.shape)
+
+
+def layernorm(x, w, b, eps, elementwise_affine=True):
+    """ops/core.py:380-386."""
+    if elementwise_affine:
+        assert w is not None and b is not None
+    else:
+        assert w is None and b is None
+    require_cuda(x, w, b)
+    x2 = _flatten_rows(x)
+    if x2.dtype != torch.float32:
+        raise RuntimeError("layernorm expects an fp32 input (the module casts with x.float())")
+    y = torch.empty_like(x2)
+    check(lib().tdb200_layer_norm_f32(ptr(x2), ptr(None if w is None else w.float()),
+                                      ptr(None if b is None else b.float()), ptr(y), x2.shape[0], x2.shape[1],
+                                      float(eps), stream_ptr(x.device)), "layernorm")
+    return y.reshape(x.shape)
+
+
+def cdiv(a: int, b: int):
+    return (a + b - 1) // b
+
+
+class Int8Linear(nn.Module):
+    """ops/core.py:391-432.  Buffers: int8_weight [N,K] int8, scale [ceil(N/128), ceil(K/128)] fp32, bias [N]."""
+
+    def __init__(self, in_features, out_features, bias=True, dtype=torch.bfloat16):
+        super().__init__()
+        self.in_features = in_features
+        self.out_features = out_features
+        row_blocks = cdiv(out_features, b=128)
+        col_blocks = cdiv(in_features, b=128)
+        self.register_buffer("int8_weight", torch.empty((out_features, in_features), dtype=torch.int8))
+        self.register_buffer("scale", torch.empty((row_blocks, col_blocks), dtype=torch.float32))
+        if bias:
+            self.register_buffer("bias", torch.empty(out_features, dtype=dtype))
+        else:
+            self.bias = None
+
+    def forward(self, x):
+        # quant + tcgen05 GEMM with the bias add fused into the epilogue (same value as `out + self.bias`)
+        return int8_linear(x, self.int8_weight, self.scale, self.bias)
+
+    @classmethod
+    def from_linear(cls, original_linear: nn.Linear, quantize: bool = True):
+        int8_layer = cls(original_linear.in_features, original_linear.out_features,
+                         bias=original_linear.bias is not None, dtype=original_linear.weight.dtype)
+        if quantize:
+            w_data = original_linear.weight.data.cuda()
+            int8_w, scale = int8_quant(w_data.contiguous())
+            int8_layer.int8_weight = int8_layer.int8_weight.to(int8_w.device)
+            int8_layer.scale = int8_layer.scale.to(int8_w.device)
+            int8_layer.int8_weight.copy_(int8_w)
+            int8_layer.scale.copy_(scale)
+            if original_linear.bias is not None:
+                int8_layer.bias = int8_layer.bias.to(int8_w.device)
+                int8_layer.bias.data.copy_(original_linear.bias.data.cuda())
+        return int8_layer
+
+
+class FastRMSNorm(nn.Module):
+    """ops/core.py:434-452.  forward == rmsnorm(x.float(), w, eps).to(x.dtype), done in ONE pass for 16-bit x."""
+
+    def __init__(self, dim: int, eps: float = 1e-5):
+        super().__init__()
+        self.dim = dim
+        self.eps = eps
+        self.register_buffer("weight", torch.ones(dim))
+
+    def forward(self, x):
+        return fast_rmsnorm(x, self.weight, self.eps)
+
+    @classmethod
+    def from_rmsnorm(cls, original_rmsnorm):
+        layer = cls(dim=original_rmsnorm.dim, eps=original_rmsnorm.eps)
+        if original_rmsnorm.weight.device != torch.device("meta"):
+            layer.weight.data.copy_(original_rmsnorm.weight.float().data)
+        return layer
+
+
+class FastLayerNorm(nn.Module):
+    """ops/core.py:454-491."""
+
+    def __init__(self, dim: int, eps: float = 1e-5, elementwise_affine: bool = False, bias: bool = True):
+        super().__init__()
+        self.dim = dim
+        self.eps = eps
+        self.elementwise_affine = elementwise_affine
+        if self.elementwise_affine:
+            self.register_buffer("weight", torch.empty(self.dim))
+            if bias:
+                self.register_buffer("bias", torch.empty(self.dim))
+            else:
+                self.bias = None
+        else:
+            self.register_parameter("weight", None)
+            self.register_parameter("bias", None)
+
+    def forward(self, x):
+        return fast_layernorm(x, self.weight, self.bias, self.eps)
+
+    @classmethod
+    def from_layernorm(cls, original_layernorm):
+        layer = cls(dim=original_layernorm.normalized_shape[0], eps=original_layernorm.eps,
+                    elementwise_affine=False if original_layernorm.weight is None else True,
+                    bias=original_layernorm.bias is not None)
+        if original_layernorm.weight is not None and original_layernorm.weight.device != torch.device("meta"):
+            layer.weight.data.copy_(original_layernorm.weight.data)
+        if original_layernorm.bias is not None and original_layernorm.bias.device != torch.device("meta"):
+            layer.bias.data.copy_(original_layernorm.bias.data)
+        return layer
+
+
+# ------------------------------------------------------------------------------------------------ fused entry points
+def _rows16(x: torch.Tensor):
+    require_cuda(x)
+    if x.dtype not in DTYPE_TAG:
+        return None
+    x2 = x.reshape(-1, x.shape[-1])
+    if not x2.is_contiguous():
+        x2 = x2.contiguous()
+    return x2
+
+
+def fast_rmsnorm(x: torch.Tensor, w: torch.Tensor, eps: float) -> torch.Tensor:
+    """FastRMSNorm.forward (ops/core.py:441-442) in one pass: T(float(x) * rstd * w)."""
+    x2 = _rows16(x)
+    if x2 is None:  # fp32 input: the reference entry point
+        return rmsnorm(x.float().contiguous(), w, eps).to(x.dtype)
+    y = torch.empty_like(x2)
+    check(lib().tdb200_rms_norm(ptr(x2), DTYPE_TAG[x.dtype], ptr(w.float()), ptr(y), x2.shape[0], x2.shape[1],
+                                float(eps), stream_ptr(x.device)), "fast_rmsnorm")
+    return y.reshape(x.shape)
+
+
+def fast_layernorm(x, w, b, eps) -> torch.Tensor:
+    """FastLayerNorm.forward (ops/core.py:477-478) in one pass."""
+    x2 = _rows16(x)
+    if x2 is None:
+        return layernorm(x.float().contiguous(), w, b, eps, w is not None).to(x.dtype)
+    y = torch.empty_like(x2)
+    check(lib().tdb200_layer_norm(ptr(x2), DTYPE_TAG[x.dtype], ptr(None if w is None else w.float()),
+                                  ptr(None if b is None else b.float()), ptr(y), x2.shape[0], x2.shape[1], float(eps),
+                                  stream_ptr(x.device)), "fast_layernorm")
+    return y.reshape(x.shape)
+
+
+def layernorm_modulate(x: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor, eps: float) -> torch.Tensor:
+    """(norm(x).float() * (1 + scale) + shift).type_as(x)  — rcm/networks/wan2pt1.py:404, scale/shift fp32 [dim]."""
+    x2 = _rows16(x)
+    assert x2 is not None, "layernorm_modulate expects a bf16/fp16 input"
+    y = torch.empty_like(x2)
+    check(lib().tdb200_layer_norm_modulate(ptr(x2), DTYPE_TAG[x.dtype], ptr(scale), ptr(shift), ptr(y), x2.shape[0],
+                                           x2.shape[1], float(eps), stream_ptr(x.device)), "layernorm_modulate")
+    return y.reshape(x.shape)
+
+
+def layernorm_modulate_quant(x: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor, eps: float):
+    """int8_quant(layernorm_modulate(x)) without materialising the 16-bit intermediate.  Returns (q, s)."""
+    x2 = _rows16(x)
+    assert x2 is not None
+    m, n = x2.shape
+    q = torch.empty((m, n), dtype=torch.int8, device=x.device)
+    s = torch.empty((cdiv(m, 128), cdiv(n, 128)), dtype=torch.float32, device=x.device)
+    stats = torch.empty((2 * m,), dtype=torch.float32, device=x.device)
+    check(lib().tdb200_layer_norm_modulate_quant(ptr(x2), DTYPE_TAG[x.dtype], ptr(scale), ptr(shift), ptr(q), ptr(s),
+                                                 ptr(stats), m, n, float(eps), stream_ptr(x.device)),
+          "layernorm_modulate_quant")
+    return q, s
+
+
+def gate_residual(x: torch.Tensor, y: torch.Tensor, gate: torch.Tensor) -> torch.Tensor:
+    """x + y * gate.type_as(x)  — rcm/networks/wan2pt1.py:405-406, gate fp32 [dim]."""
+    x2, y2 = _rows16(x), _rows16(y)
+    out = torch.empty_like(x2)
+    check(lib().tdb200_gate_residual(ptr(x2), ptr(y2), ptr(gate), ptr(out), DTYPE_TAG[x.dtype], x2.shape[0],
+                                     x2.shape[1], stream_ptr(x.device)), "gate_residual")
+    return out.reshape(x.shape)
+
+
+def rope_interleaved(x: torch.Tensor, angles: torch.Tensor) -> torch.Tensor:
+    """rope_apply (wan2pt1.py:156-178).  x [..., L, H, D] with leading batch folded into L by the caller; angles [L, D/2]."""
+    require_cuda(x, angles)
+    l, h, d = x.shape[-3:]
+    xc = x.contiguous()
+    y = torch.empty_like(xc)
+    rows = xc.numel() // (h * d)
+    assert rows == angles.shape[0], "one angle row per token row"
+    check(lib().tdb200_rope_interleaved(ptr(xc), DTYPE_TAG[x.dtype], ptr(angles), ptr(y), rows, h, d,
+                                        stream_ptr(x.device)), "rope_interleaved")
+    return y
+
+
+def rmsnorm_rope(x: torch.Tensor, w: torch.Tensor, angles: torch.Tensor, eps: float, heads: int) -> torch.Tensor:
+    """rope_apply(norm_q(x).view(L, H, D), freqs) in one pass; x [L, H*D]."""
+    require_cuda(x, w, angles)
+    xc = x.contiguous()
+    l, hd = xc.shape
+    y = torch.empty_like(xc)
+    check(lib().tdb200_rms_norm_rope(ptr(xc), DTYPE_TAG[x.dtype], ptr(w), ptr(angles), ptr(y), l, heads, hd // heads,
+                                     float(eps), stream_ptr(x.device)), "rmsnorm_rope")
+    return y
