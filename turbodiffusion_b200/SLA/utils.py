@@ -1,0 +1,77 @@
+"""Mirror of turbodiffusion/SLA/utils.py: mean_pool, get_block_map, get_cuda_arch (B200 implementation)."""
+from __future__ import annotations
+
+import torch
+
+from .._lib import DTYPE_TAG, check, lib, ptr, require_cuda, stream_ptr
+
+
+def cdiv(a, b):
+    return (a + b - 1) // b
+
+
+def get_cuda_arch(device_index):
+    """SLA/utils.py:70-71."""
+    major, minor = torch.cuda.get_device_capability(device_index)
+    return f"sm{major}{minor}"
+
+
+class QKPrep:
+    """Outputs of tdb200_sla_quant_qk for q,k in the module layout [B, L, H, D]."""
+    __slots__ = ("kmean", "q_i8", "q_scale", "k_i8", "k_scale", "q_pool", "k_pool", "mblk", "nblk")
+
+
+def quant_qk(q: torch.Tensor, k: torch.Tensor) -> QKPrep:
+    """One pass over q, two over k: key mean, pooled block means (SLA/utils.py:21-52), Sage INT8 Q / smoothed-K
+    (SLA/core.py:197-203).  q,k [B, L, H, D] contiguous bf16/fp16."""
+    require_cuda(q, k)
+    b, l, h, d = q.shape
+    assert k.shape == q.shape and q.is_contiguous() and k.is_contiguous()
+    dev = q.device
+    mblk, nblk = cdiv(l, 128), cdiv(l, 64)
+    o = QKPrep()
+    o.mblk, o.nblk = mblk, nblk
+    o.kmean = torch.empty(b, h, d, dtype=torch.float32, device=dev)
+    o.q_i8 = torch.empty(b, h, l, d, dtype=torch.int8, device=dev)
+    o.k_i8 = torch.empty(b, h, l, d, dtype=torch.int8, device=dev)
+    o.q_scale = torch.empty(b, h, mblk, dtype=torch.float32, device=dev)
+    o.k_scale = torch.empty(b, h, nblk, dtype=torch.float32, device=dev)
+    o.q_pool = torch.empty(b, h, mblk, d, dtype=q.dtype, device=dev)
+    o.k_pool = torch.empty(b, h, nblk, d, dtype=q.dtype, device=dev)
+    check(lib().tdb200_sla_quant_qk(ptr(q), ptr(k), DTYPE_TAG[q.dtype], b, l, h, d, ptr(o.kmean), ptr(o.q_i8),
+                                    ptr(o.q_scale), ptr(o.k_i8), ptr(o.k_scale), ptr(o.q_pool), ptr(o.k_pool),
+                                    stream_ptr(dev)), "sla_quant_qk")
+    return o
+
+
+def block_map_from_pools(q_pool: torch.Tensor, k_pool: torch.Tensor, topk: int):
+    """Pooled score + top-k (SLA/utils.py:59-66).  Returns (sparse_map int8 [B,H,Mblk,Nblk], lut int32 ascending)."""
+    b, h, mblk, d = q_pool.shape
+    nblk = k_pool.shape[2]
+    sparse_map = torch.empty(b, h, mblk, nblk, dtype=torch.int8, device=q_pool.device)
+    lut = torch.empty(b, h, mblk, topk, dtype=torch.int32, device=q_pool.device)
+    check(lib().tdb200_sla_block_map(ptr(q_pool), ptr(k_pool), DTYPE_TAG[q_pool.dtype], b, h, mblk, nblk, d, topk,
+                                     ptr(sparse_map), ptr(lut), stream_ptr(q_pool.device)), "sla_block_map")
+    return sparse_map, lut
+
+
+def mean_pool(x: torch.Tensor, BLK: int) -> torch.Tensor:
+    """SLA/utils.py:44-52 for x [B, H, L, D]; BLK in {64, 128}.  (Uses the fused prepass on a [B,L,H,D] view.)"""
+    assert x.is_contiguous() and BLK in (64, 128)
+    xt = x.transpose(1, 2).contiguous()
+    prep = quant_qk(xt, xt)
+    if BLK == 128:
+        return prep.q_pool
+    raise NotImplementedError("mean_pool(BLK=64) of un-smoothed keys is not part of the hot path; use quant_qk")
+
+
+def get_block_map(q: torch.Tensor, k: torch.Tensor, topk_ratio: float, BLKQ: int = 128, BLKK: int = 64):
+    """SLA/utils.py:55-67.  q,k [B, H, L, D].  Returns (sparse_map int8, lut int32 [B,H,Mblk,topk] ascending, topk).
+    NOTE the reference returns the unsorted torch.topk indices (int64) as `lut`; only the SET is defined
+    (sorted=False), and SageSLA rebuilds an ascending LUT from the map anyway (SLA/core.py:204)."""
+    assert (BLKQ, BLKK) == (128, 64), "the B200 path implements the non-sm90 block sizes (SLA/core.py:191-193)"
+    prep = quant_qk(q.transpose(1, 2).contiguous(), k.transpose(1, 2).contiguous())
+    nblk = prep.nblk
+    topk = min(nblk, int(topk_ratio * nblk))
+    sparse_map, lut = block_map_from_pools(prep.q_pool, prep.k_pool, topk)
+    return sparse_map, lut, topk

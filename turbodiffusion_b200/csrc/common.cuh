@@ -296,6 +296,13 @@ struct F16Traits<__half> {
   static __device__ __forceinline__ float round(float a) { return __half2float(__float2half_rn(a)); }
 };
 
+// bare MUFU.EX2 (no denormal fix-up code around it)
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
   for (int o = 16; o >= 1; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));

@@ -79,7 +79,7 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp >= kEpiWarps) {
-   reg_dealloc<80>();
+   reg_dealloc<56>();  // pool = 384 x 168 = 64512 regs = 256 x 224 + 128 x 56
    if (warp == kTmaWarp) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
@@ -125,7 +125,7 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
    }
   } else {
     // ------------------------------------------------------------------ dequant + epilogue warps
-    reg_alloc<216>();
+    reg_alloc<224>();
     const int q4 = warp & 3;           // TMEM lane quarter this warp may access
     const int half = warp >> 2;        // which 128-column half of the 256-wide tile
     const uint32_t lane_addr = uint32_t(q4 * 32) << 16;

@@ -1,0 +1,455 @@
+// a9 + a10. Fused SageSLA attention forward for one (128-row query block, head, batch) per CTA:
+//   block-sparse INT8 Q.K^T -> online softmax (exp2) -> bf16 P.V, then the linear branch phi(Q).KVW / (eps + phi(Q).ksum)
+//   and the merge, all in one tcgen05 kernel.
+//   reference: Sage call site turbodiffusion/SLA/core.py:231-235 (arithmetic in third-party SpargeAttn, unpinned);
+//   the in-tree statement of the same attention is the Triton kernel SLA/kernel.py:33-82 (tail masking :57-62, exp2 with
+//   qk_scale*log2e :60, row sum from unrounded P :71, P cast before P.V :73); linear branch + merge SLA/core.py:243-253.
+//
+// CTA = 6 warps.  warps 0-3: softmax, thread == query row == TMEM lane.  warp 4: TMA producer.  warp 5: MMA issuer.
+//   S[2]  TMEM cols [0,128)   int32 128x64 per buffer (double-buffered so Q.K^T of block j+1 overlaps softmax of j)
+//   O     TMEM cols [128,256) fp32 128x128, accumulated by the tensor core across all selected key blocks
+//   After the loop the S columns are reused for the linear-branch product.
+// shared memory (96 KB + LUT, two CTAs per SM): Q int8 16 KB | K int8 2x8 KB | V bf16 2x16 KB | P bf16 2x16 KB.
+//   Q/K/P (and phi(Q), KVW) are K-major 128B-swizzled; V is consumed MN-major straight from its [L, D] rows, so no
+//   transposed/quantised copy of V is ever materialised.
+// The O accumulator is only rescaled when a row maximum grows by more than 2^8 (lazy rescale): P stays <= 256, which
+// bf16/fp32 hold exactly as well as P <= 1, and the final O / l normalisation is unchanged.
+#include <type_traits>
+
+#include "common.cuh"
+#include "host_common.h"
+
+namespace {
+using namespace tdb;
+
+constexpr int D = 128;
+constexpr int BLKQ = 128, BLKK = 64;
+constexpr int kThreads = 192;
+constexpr int kSoftmaxWarps = 4, kTmaWarp = 4, kMmaWarp = 5;
+constexpr uint32_t kQ8Bytes = BLKQ * D;           // 16 KB
+constexpr uint32_t kK8Bytes = BLKK * D;           // 8 KB
+constexpr uint32_t kVBytes = BLKK * D * 2;        // 16 KB (two 64-column blocks of 8 KB)
+constexpr uint32_t kPBytes = BLKQ * BLKK * 2;     // 16 KB
+constexpr uint32_t kOffQ8 = 0;
+constexpr uint32_t kOffK8 = kOffQ8 + kQ8Bytes;
+constexpr uint32_t kOffV = kOffK8 + 2 * kK8Bytes;
+constexpr uint32_t kOffP = kOffV + 2 * kVBytes;
+constexpr uint32_t kOffBars = kOffP + 2 * kPBytes;  // 96 KB
+constexpr uint32_t kBarBytes = 256;
+constexpr uint32_t kOffLut = kOffBars + kBarBytes;
+constexpr uint32_t kTmemCols = 256;
+constexpr uint32_t kColS = 0, kColO = 128;
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kRescaleThreshold = 8.0f;         // log2 domain
+
+struct AttnParams {
+  const float* q_scale;   // [b,h,mblk]
+  const float* k_scale;   // [b,h,nblk]
+  const void* q;          // [b,l,h,d] T (linear branch)
+  const int32_t* lut;     // [b,h,mblk,topk]
+  const float* ksum;      // [b,h,d]
+  const float* proj_b;    // [d]
+  void* out;              // [b,l,h,d] T
+  int l, lk, h, mblk, nblk, topk;
+  float sm_scale;
+};
+
+enum Bar {
+  kBarQFull = 0, kBarKvFull = 1 /*2*/, kBarKvEmpty = 3 /*2*/, kBarSFull = 5 /*2*/, kBarSEmpty = 7 /*2*/,
+  kBarPFull = 9 /*2*/, kBarPEmpty = 11 /*2*/, kBarPvDone = 13, kBarKvwFull = 14, kBarPhiFull = 15, kBarOlFull = 16,
+  kNumBars = 17
+};
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads, 2)
+sla_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q8, const __grid_constant__ CUtensorMap tmap_k8,
+                    const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_kvw,
+                    AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBars);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kNumBars);
+  uint16_t* s_lut = reinterpret_cast<uint16_t*>(smem + kOffLut);                 // [topk] key-block ids
+  float* s_ksc = reinterpret_cast<float*>(smem + kOffLut + ((p.topk * 2 + 15) & ~15));  // [topk] k_scale of those blocks
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m_blk = blockIdx.x, hh = blockIdx.y, b = blockIdx.z;
+  const int bh = b * p.h + hh;
+  const int T_blocks = p.topk;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&bars[kBarQFull], 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bars[kBarKvFull + i], 1);
+      mbar_init(&bars[kBarKvEmpty + i], 1);
+      mbar_init(&bars[kBarSFull + i], 1);
+      mbar_init(&bars[kBarSEmpty + i], kSoftmaxWarps);
+      mbar_init(&bars[kBarPFull + i], kSoftmaxWarps);
+      mbar_init(&bars[kBarPEmpty + i], 1);
+    }
+    mbar_init(&bars[kBarPvDone], 1);
+    mbar_init(&bars[kBarKvwFull], 1);
+    mbar_init(&bars[kBarPhiFull], kSoftmaxWarps);
+    mbar_init(&bars[kBarOlFull], 1);
+    mbar_fence_init();
+  }
+  if (warp == kMmaWarp) tmem_alloc<kTmemCols>(tmem_slot);
+  {
+    const int32_t* lut_row = p.lut + (int64_t(bh) * p.mblk + m_blk) * p.topk;
+    const float* ksc_row = p.k_scale + int64_t(bh) * p.nblk;
+    for (int i = threadIdx.x; i < T_blocks; i += kThreads) {
+      const int blk = __ldg(lut_row + i);
+      s_lut[i] = static_cast<uint16_t>(blk);
+      s_ksc[i] = __ldg(ksc_row + blk);
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == kTmaWarp) {
+    // =============================================================== TMA producer
+    if (lane == 0) {
+      tma_prefetch_desc(&tmap_q8);
+      tma_prefetch_desc(&tmap_k8);
+      tma_prefetch_desc(&tmap_v);
+      tma_prefetch_desc(&tmap_kvw);
+      mbar_expect_tx(&bars[kBarQFull], kQ8Bytes);
+      tma_load_4d(smem + kOffQ8, &tmap_q8, &bars[kBarQFull], 0, m_blk * BLKQ, bh, 0);
+      for (int j = 0; j < T_blocks; ++j) {
+        const int st = j & 1;
+        mbar_wait(&bars[kBarKvEmpty + st], ((j >> 1) & 1) ^ 1);
+        const int blk = s_lut[j];
+        mbar_expect_tx(&bars[kBarKvFull + st], kK8Bytes + kVBytes);
+        tma_load_4d(smem + kOffK8 + st * kK8Bytes, &tmap_k8, &bars[kBarKvFull + st], 0, blk * BLKK, bh, 0);
+        uint8_t* sv = smem + kOffV + st * kVBytes;
+        tma_load_4d(sv, &tmap_v, &bars[kBarKvFull + st], 0, hh, blk * BLKK, b);
+        tma_load_4d(sv + kVBytes / 2, &tmap_v, &bars[kBarKvFull + st], 64, hh, blk * BLKK, b);
+      }
+      // all P.V reads of both V stages must have retired before KVW overwrites them
+      for (int st = 0; st < 2; ++st) {
+        const int uses = (T_blocks - st + 1) / 2;
+        if (uses > 0) mbar_wait(&bars[kBarKvEmpty + st], (uses - 1) & 1);
+      }
+      mbar_expect_tx(&bars[kBarKvwFull], 2 * kVBytes);
+      tma_load_4d(smem + kOffV, &tmap_kvw, &bars[kBarKvwFull], 0, 0, bh, 0);             // d_k 0..63  (16 KB)
+      tma_load_4d(smem + kOffV + kVBytes, &tmap_kvw, &bars[kBarKvwFull], 64, 0, bh, 0);  // d_k 64..127
+    }
+  } else if (warp == kMmaWarp) {
+    // =============================================================== MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc_qk = make_idesc(kDFmtS32, kFmtS8, kFmtS8, 0, 0, BLKQ, BLKK);
+      constexpr uint32_t idesc_pv = make_idesc(kDFmtF32, kFmtBF16, kFmtBF16, 0, 1, BLKQ, D);
+      constexpr uint32_t idesc_lin = make_idesc(kDFmtF32, kFmtBF16, kFmtBF16, 0, 0, BLKQ, D);
+      constexpr uint32_t idesc_pv16 = make_idesc(kDFmtF32, kFmtF16, kFmtF16, 0, 1, BLKQ, D);
+      constexpr uint32_t idesc_lin16 = make_idesc(kDFmtF32, kFmtF16, kFmtF16, 0, 0, BLKQ, D);
+      constexpr bool is_bf16 = sizeof(T) == 2 && std::is_same<T, __nv_bfloat16>::value;
+      const uint32_t id_pv = is_bf16 ? idesc_pv : idesc_pv16;
+      const uint32_t id_lin = is_bf16 ? idesc_lin : idesc_lin16;
+      const uint32_t sbase = smem_u32(smem);
+      const uint64_t qdesc = make_desc_kmajor_sw128(sbase + kOffQ8);
+
+      auto issue_pv = [&](int i) {
+        const int sb = i & 1;
+        mbar_wait(&bars[kBarPFull + sb], (i >> 1) & 1);
+        tc_fence_after_sync();
+        const uint64_t pdesc = make_desc_kmajor_sw128(sbase + kOffP + sb * kPBytes);
+        const uint64_t vdesc = make_desc_mnmajor_sw128(sbase + kOffV + sb * kVBytes, kVBytes / 2);
+#pragma unroll
+        for (int ks = 0; ks < BLKK / 16; ++ks)  // K=16 keys per MMA: P +32 B in its row, V +16 rows (2048 B)
+          umma_f16_ss(tmem_base + kColO, pdesc + uint64_t(ks * 2), vdesc + uint64_t(ks * 128), id_pv,
+                      (i > 0 || ks > 0) ? 1u : 0u);
+        umma_commit(&bars[kBarKvEmpty + sb]);
+        umma_commit(&bars[kBarPEmpty + sb]);
+        umma_commit(&bars[kBarPvDone]);
+      };
+
+      mbar_wait(&bars[kBarQFull], 0);
+      for (int j = 0; j < T_blocks; ++j) {
+        const int st = j & 1;
+        mbar_wait(&bars[kBarKvFull + st], (j >> 1) & 1);
+        mbar_wait(&bars[kBarSEmpty + st], ((j >> 1) & 1) ^ 1);
+        tc_fence_after_sync();
+        const uint64_t kdesc = make_desc_kmajor_sw128(sbase + kOffK8 + st * kK8Bytes);
+#pragma unroll
+        for (int ks = 0; ks < D / 32; ++ks)
+          umma_i8_ss(tmem_base + kColS + st * BLKK, qdesc + uint64_t(ks * 2), kdesc + uint64_t(ks * 2), idesc_qk,
+                     ks > 0 ? 1u : 0u);
+        umma_commit(&bars[kBarSFull + st]);
+        if (j > 0) issue_pv(j - 1);
+      }
+      issue_pv(T_blocks - 1);
+
+      // ---- linear branch: OL[128 x 128] = phi(Q)[128 x 128] . KVW^T, written over the S columns
+      mbar_wait(&bars[kBarPhiFull], 0);
+      mbar_wait(&bars[kBarKvwFull], 0);
+      tc_fence_after_sync();
+#pragma unroll
+      for (int ks = 0; ks < D / 16; ++ks) {
+        const uint32_t off = (ks >> 2) * kPBytes + (ks & 3) * 32;  // 64-wide K chunk, then +32 B per K=16 step
+        const uint64_t adesc = make_desc_kmajor_sw128(sbase + kOffP + off);
+        const uint64_t bdesc = make_desc_kmajor_sw128(sbase + kOffV + off);
+        umma_f16_ss(tmem_base + kColS, adesc, bdesc, id_lin, ks > 0 ? 1u : 0u);
+      }
+      umma_commit(&bars[kBarOlFull]);
+    }
+  } else {
+    // =============================================================== softmax / correction / epilogue warps
+    const int r = warp * 32 + lane;                     // query row inside the block == TMEM lane
+    const uint32_t lane_addr = uint32_t(warp * 32) << 16;
+    const int64_t q_row = int64_t(m_blk) * BLKQ + r;
+    const float qsc = __ldg(p.q_scale + int64_t(bh) * p.mblk + m_blk) * p.sm_scale * kLog2e;
+    constexpr float kMagicF = 12582912.0f;              // 1.5 * 2^23: as_float(0x4B400000 + i) == kMagicF + i for |i| < 2^22
+    constexpr int kMagicI = 0x4B400000;
+    uint8_t* const sP = smem + kOffP;
+
+    float m_used = -INFINITY, l_sum = 0.f;
+    for (int j = 0; j < T_blocks; ++j) {
+      const int st = j & 1;
+      const int blk = s_lut[j];
+      const float sc = qsc * s_ksc[j];
+      const int valid = p.lk - blk * BLKK;              // < 64 only in the ragged last key block
+      mbar_wait(&bars[kBarSFull + st], (j >> 1) & 1);
+      tc_fence_after_sync();
+      uint32_t s0[32], s1[32];
+      const uint32_t ts = tmem_base + lane_addr + kColS + st * BLKK;
+      tmem_ld_x32(ts, s0);
+      tmem_ld_x32(ts + 32, s1);
+      tmem_ld_wait();
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars[kBarSEmpty + st]);
+
+      // ---- row max on the raw int32 scores (sc > 0), tail columns masked
+      int mx = -2147483647 - 1;
+      if (valid >= BLKK) {
+#pragma unroll
+        for (int c = 0; c < 32; ++c) mx = max(mx, max(static_cast<int>(s0[c]), static_cast<int>(s1[c])));
+      } else {
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          if (c < valid) mx = max(mx, static_cast<int>(s0[c]));
+          if (c + 32 < valid) mx = max(mx, static_cast<int>(s1[c]));
+        }
+      }
+      const float m_blk_f = static_cast<float>(mx) * sc;
+
+      // ---- lazy rescale of the O accumulator (warp-uniform decision: tcgen05.ld/st are warp-collective)
+      const bool grow = m_blk_f > m_used + kRescaleThreshold;
+      if (j == 0) {
+        m_used = m_blk_f;
+      } else if (__any_sync(0xffffffffu, grow)) {
+        const float m_new = grow ? m_blk_f : m_used;
+        const float alpha = fast_exp2(m_used - m_new);
+        mbar_wait(&bars[kBarPvDone], (j - 1) & 1);      // P.V of block j-1 has retired; block j's is not issued yet
+        tc_fence_after_sync();
+        const uint32_t to = tmem_base + lane_addr + kColO;
+#pragma unroll
+        for (int c = 0; c < D / 32; ++c) {
+          uint32_t o[32];
+          tmem_ld_x32(to + c * 32, o);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+          tmem_st_x32(to + c * 32, o);
+        }
+        tmem_st_wait();
+        tc_fence_before_sync();
+        l_sum *= alpha;
+        m_used = m_new;
+      }
+
+      // ---- P = exp2(s*sc - m_used); int->float via the magic-number add keeps the XU pipe free for ex2
+      const float cbias = -fmaf(kMagicF, sc, m_used);
+      float psum = 0.f;
+      uint32_t pw[32];
+#pragma unroll
+      for (int c = 0; c < 32; c += 2) {
+        float p0 = fast_exp2(fmaf(__int_as_float(static_cast<int>(s0[c]) + kMagicI), sc, cbias));
+        float p1 = fast_exp2(fmaf(__int_as_float(static_cast<int>(s0[c + 1]) + kMagicI), sc, cbias));
+        if (valid < BLKK) {
+          p0 = (c < valid) ? p0 : 0.f;
+          p1 = (c + 1 < valid) ? p1 : 0.f;
+        }
+        psum += p0 + p1;
+        pw[c >> 1] = F16Traits<T>::pack(p0, p1);
+      }
+#pragma unroll
+      for (int c = 0; c < 32; c += 2) {
+        float p0 = fast_exp2(fmaf(__int_as_float(static_cast<int>(s1[c]) + kMagicI), sc, cbias));
+        float p1 = fast_exp2(fmaf(__int_as_float(static_cast<int>(s1[c + 1]) + kMagicI), sc, cbias));
+        if (valid < BLKK) {
+          p0 = (c + 32 < valid) ? p0 : 0.f;
+          p1 = (c + 33 < valid) ? p1 : 0.f;
+        }
+        psum += p0 + p1;
+        pw[16 + (c >> 1)] = F16Traits<T>::pack(p0, p1);
+      }
+      l_sum += psum;
+
+      // ---- P row -> shared memory, K-major SW128: 16-byte chunk c of row r lives at r*128 + ((c ^ (r & 7)) << 4)
+      mbar_wait(&bars[kBarPEmpty + st], ((j >> 1) & 1) ^ 1);
+      uint8_t* prow = sP + st * kPBytes + r * 128;
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        *reinterpret_cast<uint4*>(prow + ((c ^ (r & 7)) << 4)) =
+            make_uint4(pw[4 * c], pw[4 * c + 1], pw[4 * c + 2], pw[4 * c + 3]);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars[kBarPFull + st]);
+    }
+
+    // ---- linear branch operand: phi(q) = softmax over D of this thread's query row (SLA/core.py:243), rounded to T
+    float den = 1e-5f;
+    uint32_t phi[D / 2];  // holds the raw q row first, then phi(q), chunk by chunk in place
+    {
+      const T* qrow = static_cast<const T*>(p.q) + ((int64_t(b) * p.l + (q_row < p.l ? q_row : p.l - 1)) * p.h + hh) * D;
+      float qmax = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < D / 8; ++c) {
+        const uint4 raw = __ldg(reinterpret_cast<const uint4*>(qrow) + c);
+        phi[4 * c] = raw.x; phi[4 * c + 1] = raw.y; phi[4 * c + 2] = raw.z; phi[4 * c + 3] = raw.w;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          qmax = fmaxf(qmax, fmaxf(F16Traits<T>::lo(phi[4 * c + i]), F16Traits<T>::hi(phi[4 * c + i])));
+      }
+      const float qoff = qmax * kLog2e;
+      float qsum = 0.f;
+#pragma unroll
+      for (int i = 0; i < D / 2; ++i)
+        qsum += fast_exp2(fmaf(F16Traits<T>::lo(phi[i]), kLog2e, -qoff)) + fast_exp2(fmaf(F16Traits<T>::hi(phi[i]), kLog2e, -qoff));
+      const float qinv = 1.0f / qsum;
+      const float* ks = p.ksum + int64_t(bh) * D;
+#pragma unroll
+      for (int i = 0; i < D / 2; ++i) {
+        const float a = F16Traits<T>::round(fast_exp2(fmaf(F16Traits<T>::lo(phi[i]), kLog2e, -qoff)) * qinv);
+        const float c2 = F16Traits<T>::round(fast_exp2(fmaf(F16Traits<T>::hi(phi[i]), kLog2e, -qoff)) * qinv);
+        den = fmaf(a, __ldg(ks + 2 * i), den);
+        den = fmaf(c2, __ldg(ks + 2 * i + 1), den);
+        phi[i] = F16Traits<T>::pack(a, c2);
+      }
+    }
+    // all P.V MMAs retired -> the P buffers may be overwritten with phi(q) (two 64-wide K chunks of 16 KB)
+    mbar_wait(&bars[kBarPvDone], (T_blocks - 1) & 1);
+    tc_fence_after_sync();
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      uint8_t* dst = sP + (c >> 3) * kPBytes + r * 128 + (((c & 7) ^ (r & 7)) << 4);
+      *reinterpret_cast<uint4*>(dst) = make_uint4(phi[4 * c], phi[4 * c + 1], phi[4 * c + 2], phi[4 * c + 3]);
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&bars[kBarPhiFull]);
+
+    // ---- merge: out = T( O / l + OL / den + proj_b )
+    mbar_wait(&bars[kBarOlFull], 0);
+    tc_fence_after_sync();
+    const float inv_l = 1.0f / l_sum, inv_den = 1.0f / den;
+    T* orow = static_cast<T*>(p.out) + ((int64_t(b) * p.l + q_row) * p.h + hh) * D;
+#pragma unroll
+    for (int c = 0; c < D / 32; ++c) {
+      uint32_t o[32], ol[32];
+      tmem_ld_x32(tmem_base + lane_addr + kColO + c * 32, o);
+      tmem_ld_x32(tmem_base + lane_addr + kColS + c * 32, ol);
+      tmem_ld_wait();
+      if (q_row < p.l) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint32_t w[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int e = g * 8 + 2 * i;
+            const float y0 = fmaf(__uint_as_float(o[e]), inv_l, fmaf(__uint_as_float(ol[e]), inv_den, __ldg(p.proj_b + c * 32 + e)));
+            const float y1 = fmaf(__uint_as_float(o[e + 1]), inv_l, fmaf(__uint_as_float(ol[e + 1]), inv_den, __ldg(p.proj_b + c * 32 + e + 1)));
+            w[i] = F16Traits<T>::pack(y0, y1);
+          }
+          stg_v4(orow + c * 32 + g * 8, make_uint4(w[0], w[1], w[2], w[3]));
+        }
+      }
+    }
+    tc_fence_before_sync();
+  }
+
+  __syncthreads();
+  if (warp == kMmaWarp) {
+    tc_fence_after_sync();
+    tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+
+}  // namespace
+
+extern "C" int tdb200_sla_attn_fwd(const int8_t* q_i8, const float* q_scale, const int8_t* k_i8, const float* k_scale,
+                                   const void* v, const void* q, int dtype, const int32_t* lut, int64_t topk,
+                                   const void* kvw, const float* ksum, const float* proj_b, void* out, int64_t b,
+                                   int64_t l, int64_t lk, int64_t h, int64_t d, float sm_scale, void* stream) {
+  using namespace tdb;
+  if (!q_i8 || !q_scale || !k_i8 || !k_scale || !v || !q || !lut || !kvw || !ksum || !proj_b || !out)
+    return fail(TDB200_ERR_INVALID_ARG, "sla_attn_fwd: null pointer");
+  if (b <= 0 || l <= 0 || lk <= 0 || h <= 0) return fail(TDB200_ERR_INVALID_ARG, "sla_attn_fwd: bad shape");
+  if (d != D) return fail(TDB200_ERR_UNSUPPORTED, "sla_attn_fwd: head dim %lld (this build implements d=128)", (long long)d);
+  const int64_t mblk = cdiv64(l, BLKQ), nblk = cdiv64(lk, BLKK);
+  if (topk <= 0 || topk > nblk) return fail(TDB200_ERR_INVALID_ARG, "sla_attn_fwd: topk=%lld outside [1, %lld]", (long long)topk, (long long)nblk);
+  if (nblk > 65535 || h > 65535 || b > 65535) return fail(TDB200_ERR_UNSUPPORTED, "sla_attn_fwd: dimension too large");
+  const size_t lut_bytes = ((size_t(topk) * 2 + 15) & ~size_t(15)) + size_t(topk) * 4;
+  const size_t smem = 1024 + kOffLut + lut_bytes;
+  if (smem > 227 * 1024) return fail(TDB200_ERR_UNSUPPORTED, "sla_attn_fwd: topk=%lld too large for on-chip LUT", (long long)topk);
+  if (int rc = require_sm100()) return rc;
+
+  const CUtensorMapDataType t16 = dtype == TDB200_DTYPE_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  CUtensorMap tq, tk, tv, tw;
+  {
+    const uint64_t dims[4] = {uint64_t(d), uint64_t(l), uint64_t(b * h), 1};
+    const uint64_t str[3] = {uint64_t(d), uint64_t(l * d), uint64_t(b * h * l * d)};
+    const uint32_t box[4] = {D, BLKQ, 1, 1};
+    if (int rc = make_tmap_4d(&tq, q_i8, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, dims, str, box)) return rc;
+  }
+  {
+    const uint64_t dims[4] = {uint64_t(d), uint64_t(lk), uint64_t(b * h), 1};
+    const uint64_t str[3] = {uint64_t(d), uint64_t(lk * d), uint64_t(b * h * lk * d)};
+    const uint32_t box[4] = {D, BLKK, 1, 1};
+    if (int rc = make_tmap_4d(&tk, k_i8, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, dims, str, box)) return rc;
+  }
+  {
+    const uint64_t dims[4] = {uint64_t(d), uint64_t(h), uint64_t(lk), uint64_t(b)};
+    const uint64_t str[3] = {uint64_t(d * 2), uint64_t(h * d * 2), uint64_t(lk * h * d * 2)};
+    const uint32_t box[4] = {64, 1, BLKK, 1};
+    if (int rc = make_tmap_4d(&tv, v, t16, 2, dims, str, box)) return rc;
+  }
+  {
+    const uint64_t dims[4] = {uint64_t(d), uint64_t(d), uint64_t(b * h), 1};
+    const uint64_t str[3] = {uint64_t(d * 2), uint64_t(d * d * 2), uint64_t(b * h * d * d * 2)};
+    const uint32_t box[4] = {64, D, 1, 1};
+    if (int rc = make_tmap_4d(&tw, kvw, t16, 2, dims, str, box)) return rc;
+  }
+  AttnParams p;
+  p.q_scale = q_scale;
+  p.k_scale = k_scale;
+  p.q = q;
+  p.lut = lut;
+  p.ksum = ksum;
+  p.proj_b = proj_b;
+  p.out = out;
+  p.l = int(l);
+  p.lk = int(lk);
+  p.h = int(h);
+  p.mblk = int(mblk);
+  p.nblk = int(nblk);
+  p.topk = int(topk);
+  p.sm_scale = sm_scale;
+  dim3 grid(static_cast<unsigned>(mblk), static_cast<unsigned>(h), static_cast<unsigned>(b));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define TDB_ATTN(T)                                                                                                   \
+  do {                                                                                                                \
+    if (int rc = check_cuda(cudaFuncSetAttribute(sla_attn_fwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                                 static_cast<int>(smem)), "cudaFuncSetAttribute(sla_attn)"))        \
+      return rc;                                                                                                      \
+    sla_attn_fwd_kernel<T><<<grid, kThreads, smem, st>>>(tq, tk, tv, tw, p);                                          \
+    return check_launch("sla_attn_fwd_kernel");                                                                       \
+  } while (0)
+  if (dtype == TDB200_DTYPE_BF16) TDB_ATTN(__nv_bfloat16);
+  if (dtype == TDB200_DTYPE_FP16) TDB_ATTN(__half);
+#undef TDB_ATTN
+  return fail(TDB200_ERR_UNSUPPORTED, "sla_attn_fwd: dtype tag %d", dtype);
+}

@@ -1,0 +1,229 @@
+// a10 (first half). Linear-attention moments of the keys (reference: turbodiffusion/SLA/core.py:243-247):
+//   phi = softmax over the head dim (rounded to the 16-bit type),
+//   kv[b,h,dv,dk] += sum_l v[l,dv] * phi(k)[l,dk]        (stored transposed: rows = value channel, cols = key channel)
+//   ksum[b,h,dk]  += sum_l phi(k)[l,dk]
+// Both outputs are ACCUMULATED in fp32 with red.global.add (caller zeroes them), so sequence shards and the split-L
+// CTAs of one GPU combine by plain addition (and one all-reduce across GPUs).
+//
+// CTA = 6 warps, 128 key rows per tile.  warps 0-3: thread == key row: load the row, softmax over D (MUFU ex2), write
+// phi(k) into shared memory in the MN-major 128B-swizzled operand layout, then column-sum the tile for ksum.
+// warp 4: TMA loads of the V tile (consumed MN-major as the A operand: M = value channel).  warp 5: tcgen05.mma
+// kind::f16, D[128(dv) x 128(dk)] += V^T . phi(K), fp32 accumulator in TMEM across all tiles of this CTA.
+#include <type_traits>
+
+#include "common.cuh"
+#include "host_common.h"
+
+namespace {
+using namespace tdb;
+
+constexpr int D = 128;
+constexpr int kRowsPerTile = 128;
+constexpr int kThreads = 192;
+constexpr uint32_t kOperandBytes = kRowsPerTile * D * 2;  // 32 KB: two 64-channel blocks of 128 rows x 128 B
+constexpr uint32_t kBlockBytes = kOperandBytes / 2;       // 16 KB
+constexpr uint32_t kOffV = 0;                             // 2 stages
+constexpr uint32_t kOffPhi = 2 * kOperandBytes;           // 2 stages
+constexpr uint32_t kOffBars = 4 * kOperandBytes;          // 128 KB
+constexpr size_t kSmemBytes = 1024 + kOffBars + 128;
+constexpr float kLog2e = 1.4426950408889634f;
+
+enum Bar { kVFull = 0 /*2*/, kPhiFull = 2 /*2*/, kStageEmpty = 4 /*2*/, kAccFull = 6, kNumBars = 7 };
+
+struct MomParams {
+  const void* k;
+  float* kv;
+  float* ksum;
+  int l, h, tiles, splits;
+};
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads, 1)
+sla_moments_kernel(const __grid_constant__ CUtensorMap tmap_v, MomParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBars);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kNumBars);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int split = blockIdx.x, hh = blockIdx.y, b = blockIdx.z;
+  const int bh = b * p.h + hh;
+  const int my_tiles = (p.tiles - split + p.splits - 1) / p.splits;  // tiles split, split+splits, ...
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bars[kVFull + i], 1);
+      mbar_init(&bars[kPhiFull + i], 4);
+      mbar_init(&bars[kStageEmpty + i], 1);
+    }
+    mbar_init(&bars[kAccFull], 1);
+    mbar_fence_init();
+  }
+  if (warp == 5) tmem_alloc<128>(tmem_slot);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  if (my_tiles <= 0) {  // nothing to do (more splits than tiles); still release TMEM
+    __syncthreads();
+    if (warp == 5) tmem_dealloc<128>(tmem_base);
+    return;
+  }
+
+  if (warp == 4) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmap_v);
+      for (int i = 0; i < my_tiles; ++i) {
+        const int st = i & 1, tile = split + i * p.splits;
+        mbar_wait(&bars[kStageEmpty + st], ((i >> 1) & 1) ^ 1);
+        mbar_expect_tx(&bars[kVFull + st], kOperandBytes);
+        uint8_t* sv = smem + kOffV + st * kOperandBytes;
+        tma_load_4d(sv, &tmap_v, &bars[kVFull + st], 0, hh, tile * kRowsPerTile, b);
+        tma_load_4d(sv + kBlockBytes, &tmap_v, &bars[kVFull + st], 64, hh, tile * kRowsPerTile, b);
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0) {
+      constexpr bool is_bf16 = std::is_same<T, __nv_bfloat16>::value;
+      constexpr uint32_t idesc = make_idesc(kDFmtF32, is_bf16 ? kFmtBF16 : kFmtF16, is_bf16 ? kFmtBF16 : kFmtF16, 1, 1, D, D);
+      const uint32_t sbase = smem_u32(smem);
+      for (int i = 0; i < my_tiles; ++i) {
+        const int st = i & 1;
+        mbar_wait(&bars[kVFull + st], (i >> 1) & 1);
+        mbar_wait(&bars[kPhiFull + st], (i >> 1) & 1);
+        tc_fence_after_sync();
+        const uint64_t adesc = make_desc_mnmajor_sw128(sbase + kOffV + st * kOperandBytes, kBlockBytes);
+        const uint64_t bdesc = make_desc_mnmajor_sw128(sbase + kOffPhi + st * kOperandBytes, kBlockBytes);
+#pragma unroll
+        for (int ks = 0; ks < kRowsPerTile / 16; ++ks)  // K = 16 key rows per MMA: +2048 B in both operands
+          umma_f16_ss(tmem_base, adesc + uint64_t(ks * 128), bdesc + uint64_t(ks * 128), idesc, (i > 0 || ks > 0) ? 1u : 0u);
+        umma_commit(&bars[kStageEmpty + st]);
+      }
+      umma_commit(&bars[kAccFull]);
+    }
+  } else {
+    const int r = warp * 32 + lane;  // key row inside the tile; later: value channel (TMEM lane) / key channel (ksum)
+    float ksum_acc = 0.f;
+    for (int i = 0; i < my_tiles; ++i) {
+      const int st = i & 1, tile = split + i * p.splits;
+      const int64_t row = int64_t(tile) * kRowsPerTile + r;
+      uint32_t w[D / 2];
+      if (row < p.l) {
+        const uint4* src = reinterpret_cast<const uint4*>(static_cast<const T*>(p.k) + ((int64_t(b) * p.l + row) * p.h + hh) * D);
+        float mx = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < D / 8; ++c) {
+          const uint4 raw = ldg_nc_v4(src + c);
+          w[4 * c] = raw.x; w[4 * c + 1] = raw.y; w[4 * c + 2] = raw.z; w[4 * c + 3] = raw.w;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) mx = fmaxf(mx, fmaxf(F16Traits<T>::lo(w[4 * c + q]), F16Traits<T>::hi(w[4 * c + q])));
+        }
+        const float off = mx * kLog2e;
+        float sum = 0.f;
+#pragma unroll
+        for (int q = 0; q < D / 2; ++q)
+          sum += fast_exp2(fmaf(F16Traits<T>::lo(w[q]), kLog2e, -off)) + fast_exp2(fmaf(F16Traits<T>::hi(w[q]), kLog2e, -off));
+        const float inv = 1.0f / sum;
+#pragma unroll
+        for (int q = 0; q < D / 2; ++q)
+          w[q] = F16Traits<T>::pack(fast_exp2(fmaf(F16Traits<T>::lo(w[q]), kLog2e, -off)) * inv,
+                                   fast_exp2(fmaf(F16Traits<T>::hi(w[q]), kLog2e, -off)) * inv);
+      } else {
+#pragma unroll
+        for (int q = 0; q < D / 2; ++q) w[q] = 0u;
+      }
+      // stage free? (the MMA that read it two tiles ago has retired)
+      mbar_wait(&bars[kStageEmpty + st], ((i >> 1) & 1) ^ 1);
+      uint8_t* sphi = smem + kOffPhi + st * kOperandBytes;
+#pragma unroll
+      for (int c = 0; c < 16; ++c)
+        *reinterpret_cast<uint4*>(sphi + (c >> 3) * kBlockBytes + r * 128 + (((c & 7) ^ (r & 7)) << 4)) =
+            make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
+      fence_proxy_async_smem();
+      named_bar_sync(1, 128);  // all 128 rows of the tile are written (also orders the ksum reads below)
+      if (lane == 0) mbar_arrive(&bars[kPhiFull + st]);
+      // ---- ksum: thread r sums key channel r over the 128 rows of the tile
+      {
+        const uint8_t* colbase = sphi + (r >> 6) * kBlockBytes + (r & 7) * 2;
+        const int chunk = (r & 63) >> 3;
+        float s = 0.f;
+#pragma unroll 8
+        for (int rr = 0; rr < kRowsPerTile; ++rr) {
+          const unsigned short raw = *reinterpret_cast<const unsigned short*>(colbase + rr * 128 + ((chunk ^ (rr & 7)) << 4));
+          s += F16Traits<T>::lo(static_cast<uint32_t>(raw));
+        }
+        ksum_acc += s;
+      }
+    }
+    atomicAdd(p.ksum + int64_t(bh) * D + r, ksum_acc);
+    // ---- kv: TMEM lane r = value channel r, 128 key channels
+    mbar_wait(&bars[kAccFull], 0);
+    tc_fence_after_sync();
+    float* dst = p.kv + (int64_t(bh) * D + r) * D;
+#pragma unroll
+    for (int c = 0; c < D / 32; ++c) {
+      uint32_t o[32];
+      tmem_ld_x32(tmem_base + (uint32_t(warp * 32) << 16) + c * 32, o);
+      tmem_ld_wait();
+#pragma unroll
+      for (int q = 0; q < 32; q += 4)
+        red_add_v4(dst + c * 32 + q, __uint_as_float(o[q]), __uint_as_float(o[q + 1]), __uint_as_float(o[q + 2]),
+                   __uint_as_float(o[q + 3]));
+    }
+    tc_fence_before_sync();
+  }
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after_sync();
+    tmem_dealloc<128>(tmem_base);
+  }
+}
+
+}  // namespace
+
+extern "C" int tdb200_sla_linear_moments(const void* k, const void* v, int dtype, int64_t b, int64_t l, int64_t h,
+                                         int64_t d, float* kv, float* ksum, void* stream) {
+  using namespace tdb;
+  if (!k || !v || !kv || !ksum) return fail(TDB200_ERR_INVALID_ARG, "sla_linear_moments: null pointer");
+  if (b <= 0 || l <= 0 || h <= 0) return fail(TDB200_ERR_INVALID_ARG, "sla_linear_moments: bad shape");
+  if (d != D) return fail(TDB200_ERR_UNSUPPORTED, "sla_linear_moments: head dim %lld (this build implements d=128)", (long long)d);
+  if (h > 65535 || b > 65535) return fail(TDB200_ERR_UNSUPPORTED, "sla_linear_moments: h or b too large");
+  if (!aligned16(k) || !aligned16(kv)) return fail(TDB200_ERR_INVALID_ARG, "sla_linear_moments: buffers must be 16-byte aligned");
+  if (int rc = require_sm100()) return rc;
+  const CUtensorMapDataType t16 = dtype == TDB200_DTYPE_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  CUtensorMap tv;
+  {
+    const uint64_t dims[4] = {uint64_t(d), uint64_t(h), uint64_t(l), uint64_t(b)};
+    const uint64_t str[3] = {uint64_t(d * 2), uint64_t(h * d * 2), uint64_t(l * h * d * 2)};
+    const uint32_t box[4] = {64, 1, kRowsPerTile, 1};
+    if (int rc = make_tmap_4d(&tv, v, t16, 2, dims, str, box)) return rc;
+  }
+  MomParams p;
+  p.k = k;
+  p.kv = kv;
+  p.ksum = ksum;
+  p.l = int(l);
+  p.h = int(h);
+  p.tiles = int(cdiv64(l, kRowsPerTile));
+  int splits = sm_count() / int(b * h);
+  if (splits < 1) splits = 1;
+  if (splits > p.tiles) splits = p.tiles;
+  p.splits = splits;
+  dim3 grid(splits, static_cast<unsigned>(h), static_cast<unsigned>(b));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define TDB_MOM(T)                                                                                                  \
+  do {                                                                                                              \
+    if (int rc = check_cuda(cudaFuncSetAttribute(sla_moments_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                                 static_cast<int>(kSmemBytes)), "cudaFuncSetAttribute(sla_moments)")) \
+      return rc;                                                                                                    \
+    sla_moments_kernel<T><<<grid, kThreads, kSmemBytes, st>>>(tv, p);                                               \
+    return check_launch("sla_moments_kernel");                                                                      \
+  } while (0)
+  if (dtype == TDB200_DTYPE_BF16) TDB_MOM(__nv_bfloat16);
+  if (dtype == TDB200_DTYPE_FP16) TDB_MOM(__half);
+#undef TDB_MOM
+  return fail(TDB200_ERR_UNSUPPORTED, "sla_linear_moments: dtype tag %d", dtype);
+}
