@@ -69,6 +69,13 @@ int tdb200_quant_int8_block128(const void* x, int x_dtype, int64_t m, int64_t k,
  * ------------------------------------------------------------------------------------------- */
 int tdb200_gemm_w8a8(const int8_t* a_q, const float* a_s, const int8_t* b_q, const float* b_s, const void* bias,
                      void* c, int c_dtype, int64_t m, int64_t n, int64_t k, void* stream);
+/* Same GEMM with a fused activation on the output:  TDB200_EPILOGUE_GELU_TANH computes
+ * c = T(gelu_tanh(float(c_plain))) where c_plain is the value tdb200_gemm_w8a8 would store
+ * (nn.GELU(approximate="tanh") after the FFN up-projection, rcm/networks/wan2pt1.py:375). */
+#define TDB200_EPILOGUE_NONE 0
+#define TDB200_EPILOGUE_GELU_TANH 1
+int tdb200_gemm_w8a8_ex(const int8_t* a_q, const float* a_s, const int8_t* b_q, const float* b_s, const void* bias,
+                        void* c, int c_dtype, int64_t m, int64_t n, int64_t k, int epilogue, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * a3/a4. FastNorm

@@ -431,6 +431,38 @@ def ltx_rms_norm(x: torch.Tensor, eps: float = 1e-6) -> torch.Tensor:
 # =============================================================================================
 # One Wan DiT block's self-attention + FFN hot path (for bench cpu_baseline / block parity), wan2pt1.py:390-417
 # =============================================================================================
+def wan_block_forward(sd: dict, x: torch.Tensor, e0: torch.Tensor, angles: torch.Tensor, context: torch.Tensor,
+                      dim: int, heads: int, eps: float = 1e-6, topk: float = 0.1, sla_mode: str = "exact") -> torch.Tensor:
+    """WanAttentionBlock.forward (rcm/networks/wan2pt1.py:390-417) after TurboDiffusion's model surgery
+    (inference/modify_model.py:40-81), on CPU tensors.  `sd`: reference state-dict keys relative to blocks.<i>.
+    x [L, dim], e0 [6, dim] fp32, angles [L, head_dim/2], context [Lc, dim]."""
+    d = dim // heads
+    l = x.shape[0]
+
+    def lin(t, name, gelu=False):
+        y = int8_linear(t, sd[name + ".int8_weight"], sd[name + ".scale"], sd[name + ".bias"])
+        return F.gelu(y, approximate="tanh") if gelu else y
+
+    e = (sd["modulation"][0] + e0).float()
+    hmod = ln_modulate(x, e[1], e[0], eps)
+    q = fast_rmsnorm(lin(hmod, "self_attn.q"), sd["self_attn.norm_q.weight"], eps).view(l, heads, d)
+    k = fast_rmsnorm(lin(hmod, "self_attn.k"), sd["self_attn.norm_k.weight"], eps).view(l, heads, d)
+    v = lin(hmod, "self_attn.v").view(l, heads, d)
+    q, k = rope_interleaved(q, angles), rope_interleaved(k, angles)
+    a = sla_forward(q[None], k[None], v[None], sd["self_attn.attn_op.local_attn.proj_l.weight"],
+                    sd["self_attn.attn_op.local_attn.proj_l.bias"], topk, mode=sla_mode)[0].reshape(l, dim)
+    x = gate_residual(x, lin(a, "self_attn.o"), e[2])
+    hn = fast_layernorm(x, sd["norm3.weight"], sd["norm3.bias"], eps)
+    cq = fast_rmsnorm(lin(hn, "cross_attn.q"), sd["cross_attn.norm_q.weight"], eps).view(1, l, heads, d)
+    ck = fast_rmsnorm(lin(context, "cross_attn.k"), sd["cross_attn.norm_k.weight"], eps).view(1, -1, heads, d)
+    cv = lin(context, "cross_attn.v").view(1, -1, heads, d)
+    ca = dense_attention(cq.transpose(1, 2), ck.transpose(1, 2), cv.transpose(1, 2)).transpose(1, 2).reshape(l, dim)
+    x = x + lin(ca, "cross_attn.o")
+    hmod = ln_modulate(x, e[4], e[3], eps)
+    y = lin(lin(hmod, "ffn.0", gelu=True), "ffn.2")
+    return gate_residual(x, y, e[5])
+
+
 def stats(a: torch.Tensor, b: torch.Tensor) -> dict:
     """Error summary used by the parity tests."""
     a, b = a.double().flatten(), b.double().flatten()

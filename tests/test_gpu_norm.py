@@ -84,8 +84,15 @@ def test_layernorm_modulate_and_fused_quant(cuda, m, n):
     ref = O.ln_modulate(x, scale, shift, 1e-6)
     xd, sd, hd = x.to(cuda), scale.to(cuda), shift.to(cuda)
     got = ops.layernorm_modulate(xd, sd, hd, 1e-6)
-    frac, worst = _ulp_report(got.cpu(), ref)
-    assert worst <= 1.0 and frac < 2e-3, (frac, worst)
+    # The LayerNorm value is rounded to bf16 BEFORE the modulation (wan2pt1.py:404).  A 1-ulp flip of that intermediate
+    # (summation order of the row statistics) moves the result by ulp(h)*|1+scale|, which can be many ulps of a result
+    # that cancels against the shift.  Bound = one ulp of the intermediate propagated + one ulp of the result.
+    h = O.fast_layernorm(x, None, None, 1e-6).float()
+    ulp = lambda t: torch.maximum(t.abs(), torch.tensor(1e-30)).log2().floor().exp2() * 2.0 ** -7
+    bound = ulp(h) * (1 + scale).abs() + ulp(ref.float())
+    err = (got.cpu().float() - ref.float()).abs()
+    assert (err <= bound).all(), (err / bound).max()
+    assert (err > 0).float().mean() < 2e-3
     # the fused quant must equal quantising the kernel's own 16-bit output: bit-exact
     q_ref, s_ref = O.int8_quant(got.cpu())
     q, s = ops.layernorm_modulate_quant(xd, sd, hd, 1e-6)

@@ -23,6 +23,7 @@ _PROTOS = {
     "tdb200_last_error": [],
     "tdb200_quant_int8_block128": [_P, _I, _I64, _I64, _P, _P, _P],
     "tdb200_gemm_w8a8": [_P, _P, _P, _P, _P, _P, _I, _I64, _I64, _I64, _P],
+    "tdb200_gemm_w8a8_ex": [_P, _P, _P, _P, _P, _P, _I, _I64, _I64, _I64, _I, _P],
     "tdb200_rms_norm_f32": [_P, _P, _P, _I64, _I64, _F, _P],
     "tdb200_layer_norm_f32": [_P, _P, _P, _P, _I64, _I64, _F, _P],
     "tdb200_rms_norm": [_P, _I, _P, _P, _I64, _I64, _F, _P],
@@ -71,7 +72,13 @@ def lib() -> ctypes.CDLL:
     return _lib
 
 
+LAUNCHES = 0  # kernels launched through the C ABI (each entry point documents how many it enqueues)
+_KERNELS_PER_CALL = {"sla_quant_qk": 4, "layernorm_modulate_quant": 2}
+
+
 def check(rc: int, what: str) -> None:
+    global LAUNCHES
+    LAUNCHES += _KERNELS_PER_CALL.get(what, 1)
     if rc != 0:
         msg = lib().tdb200_last_error()
         raise Tdb200Error(f"{what} failed (code {rc}): {msg.decode() if msg else ''}")

@@ -1,0 +1,128 @@
+"""The Wan DiT block hot path composed from the B200 operators: a fused restatement of
+`WanAttentionBlock.forward` (turbodiffusion/rcm/networks/wan2pt1.py:390-417) as TurboDiffusion runs it after model
+surgery (inference/modify_model.py:40-81): Int8Linear everywhere in the block, FastLayerNorm / FastRMSNorm,
+SageSLA self-attention, dense SDPA cross-attention over the text tokens.
+
+Per block and per call the reference launches ~60 kernels and re-quantises the same activation three times for q/k/v;
+here the sequence is
+  LN+modulate+quant -> q/k/v GEMMs (shared int8 input) -> RMSNorm+RoPE (q,k) -> SLA (5 launches) -> quant+o GEMM
+  -> gate/residual -> LN(affine) -> cross-attention (q/k/v/o GEMMs, library SDPA on 512 keys) -> residual
+  -> LN+modulate+quant -> FFN-up GEMM (+bias+GELU fused) -> quant + FFN-down GEMM -> gate/residual.
+Weights use the reference's checkpoint format (Int8Linear buffers `int8_weight`, `scale`, `bias`).
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+import torch.nn.functional as F
+
+from . import ops
+from .SLA.core import SageSparseLinearAttention
+from .turbo_diffusion_ops import gemm_cuda_bias_gelu, gemm_cuda_swizzle_bias, quant_cuda
+
+LINEARS = ("self_attn.q", "self_attn.k", "self_attn.v", "self_attn.o", "cross_attn.q", "cross_attn.k", "cross_attn.v",
+           "cross_attn.o", "ffn.0", "ffn.2")
+
+
+def random_block_state(dim: int, ffn_dim: int, heads: int, seed: int, device, dtype=torch.bfloat16) -> Dict[str, torch.Tensor]:
+    """Random-init weights of one block in the reference's quantised state-dict layout (modify_model.py:156-183:
+    Int8Linear.from_linear quantises nn.Linear weights with int8_quant)."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    sd: Dict[str, torch.Tensor] = {}
+    shapes = {"self_attn.q": (dim, dim), "self_attn.k": (dim, dim), "self_attn.v": (dim, dim), "self_attn.o": (dim, dim),
+              "cross_attn.q": (dim, dim), "cross_attn.k": (dim, dim), "cross_attn.v": (dim, dim),
+              "cross_attn.o": (dim, dim), "ffn.0": (ffn_dim, dim), "ffn.2": (dim, ffn_dim)}
+    for name, (n, k) in shapes.items():
+        w = (torch.randn(n, k, generator=g) * (k ** -0.5)).to(dtype).to(device)
+        q, s = ops.int8_quant(w)
+        sd[name + ".int8_weight"], sd[name + ".scale"] = q, s
+        sd[name + ".bias"] = (torch.randn(n, generator=g) * 0.02).to(dtype).to(device)
+    for name in ("self_attn.norm_q", "self_attn.norm_k", "cross_attn.norm_q", "cross_attn.norm_k"):
+        sd[name + ".weight"] = (1.0 + 0.1 * torch.randn(dim, generator=g)).float().to(device)
+    sd["norm3.weight"] = (1.0 + 0.1 * torch.randn(dim, generator=g)).float().to(device)
+    sd["norm3.bias"] = (0.05 * torch.randn(dim, generator=g)).float().to(device)
+    sd["modulation"] = (torch.randn(1, 6, dim, generator=g) / dim ** 0.5).float().to(device)
+    d = dim // heads
+    sd["self_attn.attn_op.local_attn.proj_l.weight"] = (torch.randn(d, d, generator=g) * 0.05).float().to(device)
+    sd["self_attn.attn_op.local_attn.proj_l.bias"] = (torch.randn(d, generator=g) * 0.05).float().to(device)
+    return sd
+
+
+class WanBlockB200:
+    """One DiT block on the B200 operators.  `sd` uses the reference state-dict keys relative to `blocks.<i>.`."""
+
+    def __init__(self, sd: Dict[str, torch.Tensor], dim: int, heads: int, eps: float = 1e-6, topk: float = 0.1):
+        self.sd, self.dim, self.heads, self.eps = sd, dim, heads, eps
+        self.head_dim = dim // heads
+        dev = sd["modulation"].device
+        self.sla = SageSparseLinearAttention(self.head_dim, topk).to(dev)
+        with torch.no_grad():
+            self.sla.proj_l.weight.copy_(sd["self_attn.attn_op.local_attn.proj_l.weight"])
+            self.sla.proj_l.bias.copy_(sd["self_attn.attn_op.local_attn.proj_l.bias"])
+        self.attn_hook = None  # sequence-parallel wrapper installs its own attention callable here
+
+    # -- helpers -----------------------------------------------------------------------------------------------
+    def _gemm(self, xq, xs, name, dtype, gelu=False):
+        sd = self.sd
+        w_q, w_s, bias = sd[name + ".int8_weight"], sd[name + ".scale"], sd[name + ".bias"]
+        y = torch.empty(xq.shape[0], w_q.shape[0], dtype=dtype, device=xq.device)
+        (gemm_cuda_bias_gelu if gelu else gemm_cuda_swizzle_bias)(xq, xs, w_q, w_s, y, bias)
+        return y
+
+    def _linear(self, x, name, gelu=False):
+        xq, xs = quant_cuda(x)
+        return self._gemm(xq, xs, name, x.dtype, gelu)
+
+    # -- forward -------------------------------------------------------------------------------------------------
+    def forward(self, x: torch.Tensor, e0: torch.Tensor, angles: torch.Tensor, context: torch.Tensor) -> torch.Tensor:
+        """x [L, dim] 16-bit, e0 [6, dim] fp32 (time modulation), angles [L, head_dim/2] fp32, context [Lc, dim]."""
+        sd, dim, h, d, eps = self.sd, self.dim, self.heads, self.head_dim, self.eps
+        l = x.shape[0]
+        e = (sd["modulation"][0] + e0).contiguous()  # [6, dim] fp32 (wan2pt1.py:400)
+
+        # ---- self-attention (wan2pt1.py:404, 251-274)
+        xq, xs = ops.layernorm_modulate_quant(x, e[1], e[0], eps)
+        q = self._gemm(xq, xs, "self_attn.q", x.dtype)
+        k = self._gemm(xq, xs, "self_attn.k", x.dtype)
+        v = self._gemm(xq, xs, "self_attn.v", x.dtype)
+        q = ops.rmsnorm_rope(q, sd["self_attn.norm_q.weight"], angles, eps, h)
+        k = ops.rmsnorm_rope(k, sd["self_attn.norm_k.weight"], angles, eps, h)
+        attn = self.attn_hook or self.sla
+        a = attn(q.view(1, l, h, d), k.view(1, l, h, d), v.view(1, l, h, d)).reshape(l, dim)
+        y = self._linear(a, "self_attn.o")
+        x = ops.gate_residual(x, y, e[2])  # x + y * e[2] (:405-406)
+
+        # ---- cross-attention over the text tokens (:410, 277-298); dense SDPA stays a library call (512 keys)
+        hn = ops.fast_layernorm(x, sd["norm3.weight"], sd["norm3.bias"], eps)
+        cq = ops.fast_rmsnorm(self._linear(hn, "cross_attn.q"), sd["cross_attn.norm_q.weight"], eps)
+        ck = ops.fast_rmsnorm(self._linear(context, "cross_attn.k"), sd["cross_attn.norm_k.weight"], eps)
+        cv = self._linear(context, "cross_attn.v")
+        lc = context.shape[0]
+        ca = F.scaled_dot_product_attention(cq.view(1, l, h, d).transpose(1, 2), ck.view(1, lc, h, d).transpose(1, 2),
+                                            cv.view(1, lc, h, d).transpose(1, 2))
+        ca = ca.transpose(1, 2).reshape(l, dim)
+        x = x + self._linear(ca, "cross_attn.o")
+
+        # ---- FFN (:411-413)
+        hq, hs = ops.layernorm_modulate_quant(x, e[4], e[3], eps)
+        u = self._gemm(hq, hs, "ffn.0", x.dtype, gelu=True)
+        y = self._linear(u, "ffn.2")
+        return ops.gate_residual(x, y, e[5])
+
+    __call__ = forward
+
+
+class WanHotPath:
+    """`num_layers` distinct blocks = the per-denoise-step loop of WanModel.forward (wan2pt1.py:697-698)."""
+
+    def __init__(self, dim: int, ffn_dim: int, heads: int, num_layers: int, device, topk: float = 0.1, seed: int = 0,
+                 dtype=torch.bfloat16):
+        self.dim, self.heads, self.dtype = dim, heads, dtype
+        self.blocks = [WanBlockB200(random_block_state(dim, ffn_dim, heads, seed + i, device, dtype), dim, heads, topk=topk)
+                       for i in range(num_layers)]
+
+    def step(self, x, e0, angles, context):
+        for blk in self.blocks:
+            x = blk(x, e0, angles, context)
+        return x

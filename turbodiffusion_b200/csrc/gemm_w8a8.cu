@@ -40,6 +40,7 @@ struct GemmParams {
   void* c;
   int64_t m, n, k;
   int k_blocks, n_tiles, total_tiles;
+  int act;  // 0 none, 1 GELU(tanh) applied to the T-rounded (acc [+ bias]) value, result rounded to T again
 };
 
 template <typename T>
@@ -167,6 +168,15 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         if (lane == 0) mbar_arrive(&tmem_empty[buf]);
       }
 
+      // ---- optional activation: nn.GELU(approximate="tanh") evaluated in fp32 on the T-rounded pre-activation
+      //      (rcm/networks/wan2pt1.py:375 FFN), tanh via MUFU (tanh.approx, |rel err| <= 2^-11)
+      const bool act_gelu = p.act == 1;
+      auto gelu = [](float x) {
+        const float inner = 0.7978845608028654f * fmaf(0.044715f * x * x, x, x);
+        float t;
+        asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(inner));
+        return 0.5f * x * (1.0f + t);
+      };
       // ---- tile epilogue: round to T, (+bias), store this thread's 128 consecutive outputs
       const int64_t row = int64_t(m_tile) * BM + q4 * 32 + lane;
       if (row < p.m && half_active) {
@@ -181,13 +191,24 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
               const uint32_t bw[4] = {bw4.x, bw4.y, bw4.z, bw4.w};
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
-                const float y0 = F16Traits<T>::round(acc[ch * 8 + 2 * j]);
-                const float y1 = F16Traits<T>::round(acc[ch * 8 + 2 * j + 1]);
-                w[j] = F16Traits<T>::pack(y0 + F16Traits<T>::lo(bw[j]), y1 + F16Traits<T>::hi(bw[j]));
+                float y0 = F16Traits<T>::round(acc[ch * 8 + 2 * j]) + F16Traits<T>::lo(bw[j]);
+                float y1 = F16Traits<T>::round(acc[ch * 8 + 2 * j + 1]) + F16Traits<T>::hi(bw[j]);
+                if (act_gelu) {
+                  y0 = gelu(F16Traits<T>::round(y0));
+                  y1 = gelu(F16Traits<T>::round(y1));
+                }
+                w[j] = F16Traits<T>::pack(y0, y1);
               }
             } else {
 #pragma unroll
-              for (int j = 0; j < 4; ++j) w[j] = F16Traits<T>::pack(acc[ch * 8 + 2 * j], acc[ch * 8 + 2 * j + 1]);
+              for (int j = 0; j < 4; ++j) {
+                float y0 = acc[ch * 8 + 2 * j], y1 = acc[ch * 8 + 2 * j + 1];
+                if (act_gelu) {
+                  y0 = gelu(F16Traits<T>::round(y0));
+                  y1 = gelu(F16Traits<T>::round(y1));
+                }
+                w[j] = F16Traits<T>::pack(y0, y1);
+              }
             }
             stg_v4(crow + ch * 8, make_uint4(w[0], w[1], w[2], w[3]));
           }
@@ -224,7 +245,15 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cu
 extern "C" int tdb200_gemm_w8a8(const int8_t* a_q, const float* a_s, const int8_t* b_q, const float* b_s,
                                 const void* bias, void* c, int c_dtype, int64_t m, int64_t n, int64_t k,
                                 void* stream) {
+  return tdb200_gemm_w8a8_ex(a_q, a_s, b_q, b_s, bias, c, c_dtype, m, n, k, TDB200_EPILOGUE_NONE, stream);
+}
+
+extern "C" int tdb200_gemm_w8a8_ex(const int8_t* a_q, const float* a_s, const int8_t* b_q, const float* b_s,
+                                   const void* bias, void* c, int c_dtype, int64_t m, int64_t n, int64_t k,
+                                   int epilogue, void* stream) {
   using namespace tdb;
+  if (epilogue != TDB200_EPILOGUE_NONE && epilogue != TDB200_EPILOGUE_GELU_TANH)
+    return fail(TDB200_ERR_INVALID_ARG, "gemm_w8a8_ex: unknown epilogue %d", epilogue);
   if (!a_q || !a_s || !b_q || !b_s || !c) return fail(TDB200_ERR_INVALID_ARG, "gemm_w8a8: null pointer");
   if (m < 0 || n < 0 || k < 0) return fail(TDB200_ERR_INVALID_ARG, "gemm_w8a8: negative size");
   if (m == 0 || n == 0) return TDB200_OK;
@@ -252,6 +281,7 @@ extern "C" int tdb200_gemm_w8a8(const int8_t* a_q, const float* a_s, const int8_
   p.m = m;
   p.n = n;
   p.k = k;
+  p.act = epilogue;
   p.k_blocks = static_cast<int>(k / BK);
   p.n_tiles = static_cast<int>(cdiv64(n, BN));
   const int64_t total = cdiv64(m, BM) * p.n_tiles;

@@ -39,7 +39,17 @@ def quant_cuda(x: torch.Tensor, out_q: Optional[torch.Tensor] = None,
     return out_q, out_s
 
 
-def _gemm(a_q, a_s, b_q, b_s, c, bias):
+GEMM_TIMER = None  # bench.py installs a callable(m, n, k) -> context manager to time GEMM launches with CUDA events
+
+
+def _gemm(a_q, a_s, b_q, b_s, c, bias, epilogue: int = 0):
+    if GEMM_TIMER is not None:
+        with GEMM_TIMER(a_q.size(0), b_q.size(0), b_q.size(1)):
+            return _gemm_impl(a_q, a_s, b_q, b_s, c, bias, epilogue)
+    return _gemm_impl(a_q, a_s, b_q, b_s, c, bias, epilogue)
+
+
+def _gemm_impl(a_q, a_s, b_q, b_s, c, bias, epilogue: int = 0):
     require_cuda(a_q, a_s, b_q, b_s, c, bias)
     if c.dtype not in DTYPE_TAG:
         raise RuntimeError("Unsupported output data type for int8 gemm.")  # gemm.cu:62-65
@@ -49,8 +59,8 @@ def _gemm(a_q, a_s, b_q, b_s, c, bias):
     if bias is not None and bias.dtype != c.dtype:
         bias = bias.to(c.dtype)
     m, n, k = a_q.size(0), b_q.size(0), b_q.size(1)  # gemm.cu:37-39
-    check(lib().tdb200_gemm_w8a8(ptr(a_q), ptr(a_s), ptr(b_q), ptr(b_s), ptr(bias), ptr(c), DTYPE_TAG[c.dtype], m, n,
-                                 k, stream_ptr(c.device)), "gemm_cuda")
+    check(lib().tdb200_gemm_w8a8_ex(ptr(a_q), ptr(a_s), ptr(b_q), ptr(b_s), ptr(bias), ptr(c), DTYPE_TAG[c.dtype], m,
+                                    n, k, epilogue, stream_ptr(c.device)), "gemm_cuda")
 
 
 def gemm_cuda(a_q, a_s, b_q, b_s, c) -> None:
@@ -66,6 +76,11 @@ def gemm_cuda_swizzle(a_q, a_s, b_q, b_s, c, swizzle_dir: int = 1, swizzle_log: 
 def gemm_cuda_swizzle_bias(a_q, a_s, b_q, b_s, c, bias, swizzle_dir: int = 1, swizzle_log: int = 5) -> None:
     """Bias fused into the GEMM epilogue: c = T(T(acc) + bias)."""
     _gemm(a_q, a_s, b_q, b_s, c, bias)
+
+
+def gemm_cuda_bias_gelu(a_q, a_s, b_q, b_s, c, bias) -> None:
+    """c = T(gelu_tanh(T(T(acc) + bias))): Linear + nn.GELU(approximate="tanh") of the Wan FFN in one kernel."""
+    _gemm(a_q, a_s, b_q, b_s, c, bias, epilogue=1)
 
 
 def rms_norm_cuda(x: torch.Tensor, eps: float, w: Optional[torch.Tensor] = None,
