@@ -2,4 +2,4 @@
 from .core import int8_linear, int8_quant, rmsnorm, layernorm
 from .core import Int8Linear, FastRMSNorm, FastLayerNorm
 from .core import (fast_rmsnorm, fast_layernorm, layernorm_modulate, layernorm_modulate_quant, gate_residual,
-                   rope_interleaved, rmsnorm_rope, int8_linear_prequant)
+                   rope_interleaved, rmsnorm_rope, int8_linear_prequant, wan_rope_angles)

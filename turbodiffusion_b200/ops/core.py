@@ -268,3 +268,19 @@ def rmsnorm_rope(x: torch.Tensor, w: torch.Tensor, angles: torch.Tensor, eps: fl
     check(lib().tdb200_rms_norm_rope(ptr(xc), DTYPE_TAG[x.dtype], ptr(w), ptr(angles), ptr(y), l, heads, hd // heads,
                                      float(eps), stream_ptr(x.device)), "rmsnorm_rope")
     return y
+
+
+def wan_rope_angles(t: int, h: int, w: int, head_dim: int, device=None) -> torch.Tensor:
+    """Angle table [t*h*w, head_dim/2] fp32 of Wan's 3-D RoPE (VideoRopePosition3DEmb.generate_embeddings,
+    rcm/networks/wan2pt1.py:111-137): bands d_h = d_w = 2*(head_dim//6), d_t = head_dim - 2*d_h, theta 10000."""
+    dh = dw = head_dim // 6 * 2
+    dt = head_dim - 2 * dh
+
+    def freqs(dim):
+        return 1.0 / (10000.0 ** (torch.arange(0, dim, 2)[: dim // 2].float() / dim))
+
+    seq = torch.arange(max(t, h, w)).float()
+    ft, fh, fw = torch.outer(seq[:t], freqs(dt)), torch.outer(seq[:h], freqs(dh)), torch.outer(seq[:w], freqs(dw))
+    out = torch.cat([ft[:, None, None, :].expand(t, h, w, -1), fh[None, :, None, :].expand(t, h, w, -1),
+                     fw[None, None, :, :].expand(t, h, w, -1)], dim=-1).reshape(t * h * w, head_dim // 2).float().contiguous()
+    return out if device is None else out.to(device)
