@@ -123,7 +123,8 @@ int tdb200_rms_norm_rope(const void* x, int dtype, const float* w, const float* 
  * called with, SLA/core.py:181-183), d in {64, 128}.  Block sizes: BLKQ = 128 query rows, BLKK = 64 key rows
  * (the non-sm90 branch, SLA/core.py:191-193).  mblk = ceil(l/128), nblk = ceil(l/64).
  *
- * tdb200_sla_quant_qk   one pass over q and two over k:
+ * tdb200_sla_quant_qk   one pass over q [b,lq,h,d] and two over k [b,lk,h,d] (lq != lk when the query rows are one rank's
+ *     sequence shard and k is the gathered key slab; mblk = ceil(lq/128), nblk = ceil(lk/64)):
  *     kmean  [b,h,d]  fp32   = sum_l k / l  (T-rounded copy is what is subtracted, SLA/utils.py:56)
  *     q_i8   [b,h,l,d] int8, q_scale [b,h,mblk];  k_i8 [b,h,l,d] int8 of T(k - T(kmean)), k_scale [b,h,nblk]
  *                             scale = amax/127 + 1e-7, round half away from zero (SpargeAttn get_vanilla_qk_quant)
@@ -137,7 +138,7 @@ int tdb200_rms_norm_rope(const void* x, int dtype, const float* w, const float* 
  *     kvw [b,h,d(out),d(k)] T = (proj_w . kv) so that proj is folded into the moment matrix; proj_b [d] fp32.
  *     The int8 QK^T, online softmax (exp2), PV, linear branch and merge run in one tcgen05 kernel.
  * ------------------------------------------------------------------------------------------- */
-int tdb200_sla_quant_qk(const void* q, const void* k, int dtype, int64_t b, int64_t l, int64_t h, int64_t d,
+int tdb200_sla_quant_qk(const void* q, const void* k, int dtype, int64_t b, int64_t lq, int64_t lk, int64_t h, int64_t d,
                         float* kmean, int8_t* q_i8, float* q_scale, int8_t* k_i8, float* k_scale, void* q_pool,
                         void* k_pool, void* stream);
 int tdb200_sla_block_map(const void* q_pool, const void* k_pool, int dtype, int64_t b, int64_t h, int64_t mblk,

@@ -1,0 +1,90 @@
+"""N>1 host logic on CPU: world_size=2 `gloo` run of the sequence-parallel attention plumbing
+(turbodiffusion_b200/dist.py) with the CPU oracle injected as the per-rank primitives.  Checks that sharding +
+K/V all-gather + moment all-reduce reproduce the single-process result."""
+import os
+import socket
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from turbodiffusion_b200.dist import SequenceParallel, SPAttention, shard_rows  # noqa: E402
+
+
+def test_shard_rows_are_128_aligned_and_cover_everything():
+    for total, world in ((32760, 8), (75600, 8), (32760, 2), (600, 2), (1000, 4), (128, 1)):
+        covered = 0
+        for r in range(world):
+            b, e, pad = shard_rows(total, world, r)
+            assert b % 128 == 0 and pad % 128 == 0 and e - b <= pad
+            assert b == covered
+            covered = e
+        assert covered == total
+    b, e, _ = shard_rows(32760, 8, 7)
+    assert (b, e) == (7 * 4096, 32760)          # only the last rank is short (4088 rows)
+    b, e, pad = shard_rows(75600, 8, 7)
+    assert pad == 74 * 128 and e - b == 75600 - 7 * 74 * 128
+
+
+class OraclePrims:
+    """CPU implementations of the two per-rank primitives, built from the oracle."""
+
+    def __init__(self, O, proj_w, proj_b, topk):
+        self.O, self.w, self.b, self.topk = O, proj_w, proj_b, topk
+
+    def moments(self, k, v):
+        phi = torch.softmax(k.transpose(1, 2).float(), -1).to(k.dtype).float()   # [1,H,rows,D]
+        vh = v.transpose(1, 2).float()
+        return vh.transpose(-1, -2) @ phi, phi.sum(-2)                            # kv [1,H,dv,dk], ksum [1,H,D]
+
+    def attention(self, q, k_full, v_full, lk, kv, ksum):
+        O = self.O
+        qh = q.transpose(1, 2).contiguous()
+        kh = k_full[:, :lk].transpose(1, 2).contiguous()
+        vh = v_full[:, :lk].transpose(1, 2).contiguous()
+        _, lut, _ = O.get_block_map(qh, kh, self.topk, 128, 64)
+        o_s = O.sparse_attention(qh, kh, vh, lut, 128, 64)
+        pq = torch.softmax(qh.float(), -1).to(q.dtype).float()
+        num = pq @ kv.transpose(-1, -2)                                            # [1,H,rows,dv]
+        den = 1e-5 + (pq * ksum[:, :, None, :]).sum(-1, keepdim=True)
+        o_l = (num / den) @ self.w.float().t() + self.b.float()
+        return (o_s + o_l).to(q.dtype).transpose(1, 2).contiguous()
+
+
+def _worker(rank, world, port, l, h, d, topk, out_path):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import td_oracle as O
+    g = torch.Generator().manual_seed(123)
+    q = torch.randn(1, l, h, d, generator=g).bfloat16()
+    k = (torch.randn(1, l, h, d, generator=g) + torch.randn(1, 1, h, d, generator=g) * 2).bfloat16()
+    v = torch.randn(1, l, h, d, generator=g).bfloat16()
+    w, b = torch.randn(d, d, generator=g) * 0.05, torch.randn(d, generator=g) * 0.05
+    sp = SequenceParallel(l, world, rank)
+    attn = SPAttention(sp, OraclePrims(O, w, b, topk))
+    sl = slice(sp.row_begin, sp.row_end)
+    out_local = attn(q[:, sl].contiguous(), k[:, sl].contiguous(), v[:, sl].contiguous())
+    full = sp.gather_rows(out_local[0].reshape(sp.local_rows, h * d))
+    if rank == 0:
+        ref = O.sla_forward(q, k, v, w, b, topk, mode="exact")[0].reshape(l, h * d)
+        torch.save({"stats": O.stats(full, ref), "rows": [sp.row_begin, sp.row_end]}, out_path)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("l", [600, 1000])
+def test_sequence_parallel_attention_gloo_world2(tmp_path, l):
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    out = str(tmp_path / "sp.pt")
+    mp.spawn(_worker, args=(2, port, l, 2, 64, 0.3, out), nprocs=2, join=True)
+    res = torch.load(out)
+    assert res["stats"]["rel_l2"] < 5e-3, res  # only bf16 output rounding differs from the single-process oracle

@@ -21,24 +21,27 @@ class QKPrep:
     __slots__ = ("kmean", "q_i8", "q_scale", "k_i8", "k_scale", "q_pool", "k_pool", "mblk", "nblk")
 
 
-def quant_qk(q: torch.Tensor, k: torch.Tensor) -> QKPrep:
+def quant_qk(q: torch.Tensor, k: torch.Tensor, lk: int = None) -> QKPrep:
     """One pass over q, two over k: key mean, pooled block means (SLA/utils.py:21-52), Sage INT8 Q / smoothed-K
-    (SLA/core.py:197-203).  q,k [B, L, H, D] contiguous bf16/fp16."""
+    (SLA/core.py:197-203).  q [B, Lq, H, D], k [B, >=lk, H, D] contiguous bf16/fp16; only the first `lk` key rows are
+    used (sequence-parallel callers pass the gathered, tail-padded key slab)."""
     require_cuda(q, k)
-    b, l, h, d = q.shape
-    assert k.shape == q.shape and q.is_contiguous() and k.is_contiguous()
+    b, lq, h, d = q.shape
+    lk = k.shape[1] if lk is None else lk
+    assert k.shape[0] == b and k.shape[2:] == q.shape[2:] and lk <= k.shape[1]
+    assert q.is_contiguous() and k.is_contiguous() and (b == 1 or lk == k.shape[1])
     dev = q.device
-    mblk, nblk = cdiv(l, 128), cdiv(l, 64)
+    mblk, nblk = cdiv(lq, 128), cdiv(lk, 64)
     o = QKPrep()
     o.mblk, o.nblk = mblk, nblk
     o.kmean = torch.empty(b, h, d, dtype=torch.float32, device=dev)
-    o.q_i8 = torch.empty(b, h, l, d, dtype=torch.int8, device=dev)
-    o.k_i8 = torch.empty(b, h, l, d, dtype=torch.int8, device=dev)
+    o.q_i8 = torch.empty(b, h, lq, d, dtype=torch.int8, device=dev)
+    o.k_i8 = torch.empty(b, h, lk, d, dtype=torch.int8, device=dev)
     o.q_scale = torch.empty(b, h, mblk, dtype=torch.float32, device=dev)
     o.k_scale = torch.empty(b, h, nblk, dtype=torch.float32, device=dev)
     o.q_pool = torch.empty(b, h, mblk, d, dtype=q.dtype, device=dev)
     o.k_pool = torch.empty(b, h, nblk, d, dtype=q.dtype, device=dev)
-    check(lib().tdb200_sla_quant_qk(ptr(q), ptr(k), DTYPE_TAG[q.dtype], b, l, h, d, ptr(o.kmean), ptr(o.q_i8),
+    check(lib().tdb200_sla_quant_qk(ptr(q), ptr(k), DTYPE_TAG[q.dtype], b, lq, lk, h, d, ptr(o.kmean), ptr(o.q_i8),
                                     ptr(o.q_scale), ptr(o.k_i8), ptr(o.k_scale), ptr(o.q_pool), ptr(o.k_pool),
                                     stream_ptr(dev)), "sla_quant_qk")
     return o

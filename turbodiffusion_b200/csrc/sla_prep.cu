@@ -148,9 +148,9 @@ __global__ void __launch_bounds__(ROWS* D / 64) pool_quant_kernel(const T* __res
 }
 
 template <typename T, int D>
-int run(const void* q, const void* k, int64_t b, int64_t l, int64_t h, float* kmean, int8_t* q_i8, float* q_scale,
-        int8_t* k_i8, float* k_scale, void* q_pool, void* k_pool, cudaStream_t st) {
-  const int mblk = static_cast<int>(cdiv64(l, 128)), nblk = static_cast<int>(cdiv64(l, 64));
+int run(const void* q, const void* k, int64_t b, int64_t lq, int64_t l, int64_t h, float* kmean, int8_t* q_i8,
+        float* q_scale, int8_t* k_i8, float* k_scale, void* q_pool, void* k_pool, cudaStream_t st) {
+  const int mblk = static_cast<int>(cdiv64(lq, 128)), nblk = static_cast<int>(cdiv64(l, 64));
   const int chunks = static_cast<int>(cdiv64(l, kMeanRows));
   float* partial = reinterpret_cast<float*>(k_i8);  // scratch: chunks*D*4 bytes per head <= l*D bytes (l*D/64 floats)
   dim3 g1(chunks, static_cast<unsigned>(h), static_cast<unsigned>(b));
@@ -160,7 +160,7 @@ int run(const void* q, const void* k, int64_t b, int64_t l, int64_t h, float* km
   if (int rc = check_launch("kmean_final_kernel")) return rc;
   dim3 gq(mblk, static_cast<unsigned>(h), static_cast<unsigned>(b));
   pool_quant_kernel<T, D, 128, false><<<gq, 128 * D / 64, 0, st>>>(static_cast<const T*>(q), nullptr, q_i8, q_scale,
-                                                                   static_cast<T*>(q_pool), l, static_cast<int>(h), mblk);
+                                                                   static_cast<T*>(q_pool), lq, static_cast<int>(h), mblk);
   if (int rc = check_launch("pool_quant_kernel<q>")) return rc;
   dim3 gk(nblk, static_cast<unsigned>(h), static_cast<unsigned>(b));
   pool_quant_kernel<T, D, 64, true><<<gk, 64 * D / 64, 0, st>>>(static_cast<const T*>(k), kmean, k_i8, k_scale,
@@ -170,20 +170,20 @@ int run(const void* q, const void* k, int64_t b, int64_t l, int64_t h, float* km
 
 }  // namespace
 
-extern "C" int tdb200_sla_quant_qk(const void* q, const void* k, int dtype, int64_t b, int64_t l, int64_t h, int64_t d,
-                                   float* kmean, int8_t* q_i8, float* q_scale, int8_t* k_i8, float* k_scale,
+extern "C" int tdb200_sla_quant_qk(const void* q, const void* k, int dtype, int64_t b, int64_t lq, int64_t l, int64_t h,
+                                   int64_t d, float* kmean, int8_t* q_i8, float* q_scale, int8_t* k_i8, float* k_scale,
                                    void* q_pool, void* k_pool, void* stream) {
   using namespace tdb;
   if (!q || !k || !kmean || !q_i8 || !q_scale || !k_i8 || !k_scale || !q_pool || !k_pool)
     return fail(TDB200_ERR_INVALID_ARG, "sla_quant_qk: null pointer");
-  if (b <= 0 || l <= 0 || h <= 0) return fail(TDB200_ERR_INVALID_ARG, "sla_quant_qk: bad shape");
+  if (b <= 0 || l <= 0 || lq <= 0 || h <= 0) return fail(TDB200_ERR_INVALID_ARG, "sla_quant_qk: bad shape");
   if (d != 64 && d != 128) return fail(TDB200_ERR_UNSUPPORTED, "sla_quant_qk: head dim %lld (64 or 128, SLA/core.py:207)", (long long)d);
   if (h > 65535 || b > 65535) return fail(TDB200_ERR_UNSUPPORTED, "sla_quant_qk: h or b too large");
   if (!aligned16(q) || !aligned16(k) || !aligned16(q_i8) || !aligned16(k_i8))
     return fail(TDB200_ERR_INVALID_ARG, "sla_quant_qk: buffers must be 16-byte aligned");
   if (int rc = require_sm100()) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-#define TDB_RUN(T, D) return run<T, D>(q, k, b, l, h, kmean, q_i8, q_scale, k_i8, k_scale, q_pool, k_pool, st)
+#define TDB_RUN(T, D) return run<T, D>(q, k, b, lq, l, h, kmean, q_i8, q_scale, k_i8, k_scale, q_pool, k_pool, st)
   if (dtype == TDB200_DTYPE_BF16) {
     if (d == 128) TDB_RUN(__nv_bfloat16, 128);
     TDB_RUN(__nv_bfloat16, 64);
