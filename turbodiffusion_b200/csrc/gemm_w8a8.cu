@@ -31,7 +31,8 @@ constexpr uint32_t kATile = BM * BK;            // 16 KB
 constexpr uint32_t kBTile = BN * BK;            // 32 KB
 constexpr uint32_t kStageBytes = kATile + kBTile;
 constexpr uint32_t kTmemCols = 512;             // 2 accumulator buffers x 256 int32 columns
-constexpr size_t kSmemBytes = 1024 /*align slack*/ + size_t(kStages) * kStageBytes + 256 /*barriers*/;
+constexpr uint32_t kCStageBytes = 32 * 128;     // per-warp output staging: 32 rows x 64 columns of T (swizzled)
+constexpr size_t kSmemBytes = 1024 /*align slack*/ + size_t(kStages) * kStageBytes + kEpiWarps * kCStageBytes + 256 /*barriers*/;
 
 struct GemmParams {
   const float* a_s;
@@ -39,16 +40,21 @@ struct GemmParams {
   const void* bias;
   void* c;
   int64_t m, n, k;
-  int k_blocks, n_tiles, total_tiles;
+  int k_blocks, n_tiles, m_tiles, total_tiles;  // total_tiles: tiles, or tile PAIRS in the cluster variant
   int act;  // 0 none, 1 GELU(tanh) applied to the T-rounded (acc [+ bias]) value, result rounded to T again
 };
 
-template <typename T>
+// kCluster: CTAs are launched as clusters of 2 that work on vertically adjacent tiles (m, n) and (m+1, n).  Each CTA
+// loads its own A tile and HALF of the shared B tile, multicasting that half to both CTAs: 32 KB instead of 48 KB cross
+// the L2->SM fabric per CTA and K-block.  A stage may only be refilled when BOTH CTAs' MMAs have released it, so the
+// stage-empty barriers count 2 arrivals and the MMA warps commit to both CTAs.
+template <typename T, bool kCluster>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + size_t(kStages) * kStageBytes);
+  uint8_t* c_stage = smem + size_t(kStages) * kStageBytes;  // [kEpiWarps][32 rows][128 B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(c_stage + kEpiWarps * kCStageBytes);
   uint64_t* full_bar = bars;                      // [kStages]  TMA -> MMA
   uint64_t* empty_bar = bars + kStages;           // [kStages]  MMA -> TMA
   uint64_t* tmem_full = bars + 2 * kStages;       // [2]        MMA -> epilogue
@@ -57,11 +63,19 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t crank = kCluster ? cluster_ctarank() : 0u;
+  // work items: single tiles, or vertical tile pairs (one per cluster) in the cluster variant
+  const int work_first = kCluster ? int(blockIdx.x >> 1) : int(blockIdx.x);
+  const int work_stride = kCluster ? int(gridDim.x >> 1) : int(gridDim.x);
+  auto tile_of = [&](int work, int& m_tile, int& n_tile) {
+    n_tile = work % p.n_tiles;
+    m_tile = kCluster ? 2 * (work / p.n_tiles) + int(crank) : work / p.n_tiles;
+  };
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], 1);
+      mbar_init(&empty_bar[i], kCluster ? 2 : 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
@@ -75,7 +89,7 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     tma_prefetch_desc(&tmap_b);
   }
   tc_fence_before_sync();
-  __syncthreads();
+  if (kCluster) cluster_sync_all(); else __syncthreads();  // barrier inits visible cluster-wide before any remote arrive
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -85,15 +99,20 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const int m_tile = tile / p.n_tiles, n_tile = tile % p.n_tiles;
+      for (int work = work_first; work < p.total_tiles; work += work_stride) {
+        int m_tile, n_tile;
+        tile_of(work, m_tile, n_tile);
         for (int kb = 0; kb < p.k_blocks; ++kb, ++it) {
           const uint32_t stage = it % kStages, phase = (it / kStages) & 1u;
           mbar_wait(&empty_bar[stage], phase ^ 1u);
           uint8_t* sa = smem + size_t(stage) * kStageBytes;
           mbar_expect_tx(&full_bar[stage], kStageBytes);
           tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BK, m_tile * BM);
-          tma_load_2d(sa + kATile, &tmap_b, &full_bar[stage], kb * BK, n_tile * BN);
+          if (kCluster)  // my half (128 rows) of the shared B tile, delivered to both CTAs
+            tma_load_2d_mcast(sa + kATile + crank * (kBTile / 2), &tmap_b, &full_bar[stage], kb * BK,
+                              n_tile * BN + int(crank) * (BN / 2), uint16_t(3));
+          else
+            tma_load_2d(sa + kATile, &tmap_b, &full_bar[stage], kb * BK, n_tile * BN);
         }
       }
     }
@@ -102,7 +121,7 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(kDFmtS32, kFmtS8, kFmtS8, 0, 0, BM, BN);
       uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      for (int work = work_first; work < p.total_tiles; work += work_stride) {
         for (int kb = 0; kb < p.k_blocks; ++kb, ++it) {
           const uint32_t stage = it % kStages, phase = (it / kStages) & 1u;
           const uint32_t buf = it & 1u, bphase = (it >> 1) & 1u;
@@ -118,7 +137,7 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             // advance 32 bytes (one K=32 int8 slice) inside the 128B swizzle row: +2 in 16-byte units
             umma_i8_ss(d, adesc + uint64_t(ks * 2), bdesc + uint64_t(ks * 2), idesc, ks > 0 ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);
+          if (kCluster) umma_commit_mcast(&empty_bar[stage], uint16_t(3)); else umma_commit(&empty_bar[stage]);
           umma_commit(&tmem_full[buf]);
         }
       }
@@ -131,37 +150,39 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const int half = warp >> 2;        // which 128-column half of the 256-wide tile
     const uint32_t lane_addr = uint32_t(q4 * 32) << 16;
     uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      const int m_tile = tile / p.n_tiles, n_tile = tile % p.n_tiles;
+    for (int work = work_first; work < p.total_tiles; work += work_stride) {
+      int m_tile, n_tile;
+      tile_of(work, m_tile, n_tile);
       const int64_t col0 = int64_t(n_tile) * BN + half * 128;
       const bool half_active = col0 < p.n;
-      const float* as_row = p.a_s + int64_t(m_tile) * p.k_blocks;
+      const float* as_row = p.a_s + int64_t(m_tile < p.m_tiles ? m_tile : p.m_tiles - 1) * p.k_blocks;  // odd tail pair
       const float* bs_row = p.b_s + (half_active ? (col0 >> 7) : 0) * p.k_blocks;
 
       float acc[128];
 #pragma unroll
       for (int j = 0; j < 128; ++j) acc[j] = 0.0f;
 
-      float scale_next = __ldg(as_row) * __ldg(bs_row);
+      // block scales are fetched one K-block ahead and only multiplied when used, so the global-load latency hides
+      // behind the previous K-block's dequant instead of stalling in front of the barrier wait
+      float as_next = __ldg(as_row), bs_next = __ldg(bs_row);
       for (int kb = 0; kb < p.k_blocks; ++kb, ++it) {
         const uint32_t buf = it & 1u, bphase = (it >> 1) & 1u;
-        const float scale = scale_next;
-        if (kb + 1 < p.k_blocks) scale_next = __ldg(as_row + kb + 1) * __ldg(bs_row + kb + 1);
+        const float scale = as_next * bs_next;
+        if (kb + 1 < p.k_blocks) {
+          as_next = __ldg(as_row + kb + 1);
+          bs_next = __ldg(bs_row + kb + 1);
+        }
         mbar_wait(&tmem_full[buf], bphase);
         tc_fence_after_sync();
         const uint32_t t0 = tmem_base + lane_addr + buf * BN + half * 128;
 #pragma unroll
-        for (int c = 0; c < 4; c += 2) {
-          uint32_t r0[32], r1[32];
-          tmem_ld_x32(t0 + c * 32, r0);
-          tmem_ld_x32(t0 + c * 32 + 32, r1);
+        for (int c = 0; c < 2; ++c) {
+          uint32_t r[64];
+          tmem_ld_x64(t0 + c * 64, r);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            acc[c * 32 + j] = fmaf(__int2float_rn(static_cast<int>(r0[j])), scale, acc[c * 32 + j]);
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            acc[c * 32 + 32 + j] = fmaf(__int2float_rn(static_cast<int>(r1[j])), scale, acc[c * 32 + 32 + j]);
+          for (int j = 0; j < 64; ++j)
+            acc[c * 64 + j] = fmaf(__int2float_rn(static_cast<int>(r[j])), scale, acc[c * 64 + j]);
         }
         tc_fence_before_sync();
         __syncwarp();
@@ -177,67 +198,84 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(inner));
         return 0.5f * x * (1.0f + t);
       };
-      // ---- tile epilogue: round to T, (+bias), store this thread's 128 consecutive outputs
-      const int64_t row = int64_t(m_tile) * BM + q4 * 32 + lane;
-      if (row < p.m && half_active) {
-        T* crow = static_cast<T*>(p.c) + row * p.n + col0;
-        const T* bias = static_cast<const T*>(p.bias);
+      // ---- tile epilogue: round to T, (+bias), (GELU), then write through a per-warp swizzled smem buffer so that
+      //      every global store instruction covers four complete 128-byte lines (a thread owns one ROW of the tile,
+      //      so storing straight from registers would touch 32 different rows per instruction).
+      const int64_t row0 = int64_t(m_tile) * BM + q4 * 32;
+      const T* bias = static_cast<const T*>(p.bias);
+      uint8_t* stage = c_stage + warp * kCStageBytes;
 #pragma unroll
-        for (int ch = 0; ch < 16; ++ch) {
-          if (col0 + ch * 8 < p.n) {  // n % 8 == 0: a chunk is fully in or out
-            uint32_t w[4];
-            if (bias != nullptr) {
-              const uint4 bw4 = *reinterpret_cast<const uint4*>(bias + col0 + ch * 8);
-              const uint32_t bw[4] = {bw4.x, bw4.y, bw4.z, bw4.w};
+      for (int pass = 0; pass < 2; ++pass) {  // 64 columns per pass
+        const int64_t colp = col0 + pass * 64;
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                float y0 = F16Traits<T>::round(acc[ch * 8 + 2 * j]) + F16Traits<T>::lo(bw[j]);
-                float y1 = F16Traits<T>::round(acc[ch * 8 + 2 * j + 1]) + F16Traits<T>::hi(bw[j]);
-                if (act_gelu) {
-                  y0 = gelu(F16Traits<T>::round(y0));
-                  y1 = gelu(F16Traits<T>::round(y1));
-                }
-                w[j] = F16Traits<T>::pack(y0, y1);
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                float y0 = acc[ch * 8 + 2 * j], y1 = acc[ch * 8 + 2 * j + 1];
-                if (act_gelu) {
-                  y0 = gelu(F16Traits<T>::round(y0));
-                  y1 = gelu(F16Traits<T>::round(y1));
-                }
-                w[j] = F16Traits<T>::pack(y0, y1);
-              }
-            }
-            stg_v4(crow + ch * 8, make_uint4(w[0], w[1], w[2], w[3]));
+        for (int ch = 0; ch < 8; ++ch) {
+          uint32_t w[4];
+          uint32_t bw[4] = {0u, 0u, 0u, 0u};
+          const bool chunk_in = half_active && colp + ch * 8 < p.n;  // n % 8 == 0: a chunk is fully in or out
+          if (bias != nullptr && chunk_in) {
+            const uint4 b4 = *reinterpret_cast<const uint4*>(bias + colp + ch * 8);
+            bw[0] = b4.x; bw[1] = b4.y; bw[2] = b4.z; bw[3] = b4.w;
           }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float y0 = acc[pass * 64 + ch * 8 + 2 * j], y1 = acc[pass * 64 + ch * 8 + 2 * j + 1];
+            if (bias != nullptr) {
+              y0 = F16Traits<T>::round(y0) + F16Traits<T>::lo(bw[j]);
+              y1 = F16Traits<T>::round(y1) + F16Traits<T>::hi(bw[j]);
+            }
+            if (act_gelu) {
+              y0 = gelu(F16Traits<T>::round(y0));
+              y1 = gelu(F16Traits<T>::round(y1));
+            }
+            w[j] = F16Traits<T>::pack(y0, y1);
+          }
+          *reinterpret_cast<uint4*>(stage + lane * 128 + ((ch ^ (lane & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
         }
+        __syncwarp();
+        // read back: instruction i moves rows 4i..4i+3; 8 lanes cover one row's 128 contiguous bytes
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rr = 4 * i + (lane >> 3), cc = lane & 7;
+          const uint4 v = *reinterpret_cast<const uint4*>(stage + rr * 128 + ((cc ^ (rr & 7)) << 4));
+          const int64_t grow = row0 + rr;
+          if (half_active && grow < p.m && colp + cc * 8 < p.n)
+            stg_v4(static_cast<T*>(p.c) + grow * p.n + colp + cc * 8, v);
+        }
+        __syncwarp();
       }
     }
   }
 
   tc_fence_before_sync();
-  __syncthreads();
+  if (kCluster) cluster_sync_all(); else __syncthreads();  // the peer may still multicast into / arrive on this CTA
   if (warp == kMmaWarp) {
     tc_fence_after_sync();
     tmem_dealloc<kTmemCols>(tmem_base);
   }
 }
 
-template <typename T>
+template <typename T, bool kCluster>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
-  static bool attr_set = false;  // per-process; the attribute is per-function and idempotent
-  if (!attr_set) {
-    if (int rc = check_cuda(cudaFuncSetAttribute(gemm_w8a8_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                 static_cast<int>(kSmemBytes)),
-                            "cudaFuncSetAttribute(gemm_w8a8)"))
-      return rc;
-    attr_set = true;
-  }
-  const int grid = p.total_tiles < sm_count() ? p.total_tiles : sm_count();
-  gemm_w8a8_kernel<T><<<grid, kThreads, kSmemBytes, st>>>(ta, tb, p);
-  return check_launch("gemm_w8a8_kernel");
+  auto kern = gemm_w8a8_kernel<T, kCluster>;
+  if (int rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemBytes)),
+                          "cudaFuncSetAttribute(gemm_w8a8)"))
+    return rc;
+  int grid = kCluster ? 2 * p.total_tiles : p.total_tiles;
+  const int cap = kCluster ? (sm_count() & ~1) : sm_count();
+  if (grid > cap) grid = cap;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = kSmemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kCluster ? 2 : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return check_cuda(cudaLaunchKernelEx(&cfg, kern, ta, tb, p), "gemm_w8a8_kernel launch");
 }
 
 }  // namespace
@@ -267,10 +305,13 @@ extern "C" int tdb200_gemm_w8a8_ex(const int8_t* a_q, const float* a_s, const in
     return fail(TDB200_ERR_UNSUPPORTED, "gemm_w8a8: dimension exceeds int32 TMA coordinates");
   if (int rc = require_sm100()) return rc;
 
+  const int64_t m_tiles = cdiv64(m, BM);
+  const bool use_cluster = m_tiles >= 2;  // pairs of vertically adjacent tiles share the B tile by TMA multicast
   CUtensorMap ta, tb;
   if (int rc = make_tmap_2d(&ta, a_q, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, uint64_t(k), uint64_t(m), uint64_t(k), BK, BM))
     return rc;
-  if (int rc = make_tmap_2d(&tb, b_q, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, uint64_t(k), uint64_t(n), uint64_t(k), BK, BN))
+  if (int rc = make_tmap_2d(&tb, b_q, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, uint64_t(k), uint64_t(n), uint64_t(k), BK,
+                            use_cluster ? BN / 2 : BN))
     return rc;
 
   GemmParams p;
@@ -284,11 +325,14 @@ extern "C" int tdb200_gemm_w8a8_ex(const int8_t* a_q, const float* a_s, const in
   p.act = epilogue;
   p.k_blocks = static_cast<int>(k / BK);
   p.n_tiles = static_cast<int>(cdiv64(n, BN));
-  const int64_t total = cdiv64(m, BM) * p.n_tiles;
-  if (total > (int64_t(1) << 30)) return fail(TDB200_ERR_UNSUPPORTED, "gemm_w8a8: too many tiles");
+  p.m_tiles = static_cast<int>(m_tiles);
+  const int64_t total = (use_cluster ? cdiv64(m_tiles, 2) : m_tiles) * p.n_tiles;
+  if (total > (int64_t(1) << 29)) return fail(TDB200_ERR_UNSUPPORTED, "gemm_w8a8: too many tiles");
   p.total_tiles = static_cast<int>(total);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (c_dtype == TDB200_DTYPE_BF16) return launch<__nv_bfloat16>(ta, tb, p, st);
-  if (c_dtype == TDB200_DTYPE_FP16) return launch<__half>(ta, tb, p, st);
+  if (c_dtype == TDB200_DTYPE_BF16)
+    return use_cluster ? launch<__nv_bfloat16, true>(ta, tb, p, st) : launch<__nv_bfloat16, false>(ta, tb, p, st);
+  if (c_dtype == TDB200_DTYPE_FP16)
+    return use_cluster ? launch<__half, true>(ta, tb, p, st) : launch<__half, false>(ta, tb, p, st);
   return fail(TDB200_ERR_UNSUPPORTED, "gemm_w8a8: output dtype tag %d (bf16/fp16 only, gemm.cu:41-65)", c_dtype);
 }

@@ -15,7 +15,6 @@
 namespace {
 using namespace tdb;
 
-constexpr int kMaxChunks = 8;  // 16-byte chunks per thread -> N <= 8 * 8 * 256 = 16384 (16-bit) / 4*8*256 = 8192... see launch
 
 template <int kThreads>
 __device__ __forceinline__ float block_sum(float v, float* red) {
@@ -67,6 +66,16 @@ template <>
 struct Chunk<__nv_bfloat16> : Chunk16<__nv_bfloat16> {};
 template <>
 struct Chunk<__half> : Chunk16<__half> {};
+
+// E consecutive fp32 parameters (E = 4 or 8, 16-byte aligned) with 128-bit loads
+template <int E>
+__device__ __forceinline__ void load_params(const float* __restrict__ p, float* out) {
+#pragma unroll
+  for (int i = 0; i < E / 4; ++i) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(p) + i);
+    out[4 * i] = v.x; out[4 * i + 1] = v.y; out[4 * i + 2] = v.z; out[4 * i + 3] = v.w;
+  }
+}
 
 enum NormKind { kRms = 0, kLayer = 1 };
 enum PostKind { kPostNone = 0, kPostModulate = 1, kPostRope = 2, kPostStatsOnly = 3 };
@@ -164,26 +173,34 @@ __global__ void __launch_bounds__(kThreads) row_norm_kernel(RowParams p) {
       float f[E];
       Chunk<T>::unpack(raw[i], f);
       const int col = c * E;
+      float wv[E], bv[E], scv[E], shv[E];
+      if (p.w != nullptr) load_params<E>(p.w + col, wv);
+      if (p.w != nullptr && p.b != nullptr) load_params<E>(p.b + col, bv);
+      if (kPost == kPostModulate) {
+        load_params<E>(p.scale + col, scv);
+        load_params<E>(p.shift + col, shv);
+      }
 #pragma unroll
       for (int j = 0; j < E; ++j) {
         float v = (kNorm == kRms) ? __fmul_rn(f[j], rstd) : __fmul_rn(f[j] - mean, rstd);
         if (p.w != nullptr) {
-          v = __fmul_rn(v, __ldg(p.w + col + j));
-          if (p.b != nullptr) v = __fadd_rn(v, __ldg(p.b + col + j));
+          v = __fmul_rn(v, wv[j]);
+          if (p.b != nullptr) v = __fadd_rn(v, bv[j]);
         }
         if (kPost == kPostModulate) {
           v = Chunk<T>::round(v);  // norm output is cast to T before the modulation (wan2pt1.py:404)
-          v = __fadd_rn(__fmul_rn(v, __fadd_rn(1.0f, __ldg(p.scale + col + j))), __ldg(p.shift + col + j));
+          v = __fadd_rn(__fmul_rn(v, __fadd_rn(1.0f, scv[j])), shv[j]);
         }
         f[j] = v;
       }
       if (kPost == kPostRope) {
         // pairs (2i, 2i+1) inside a head of width d; angle index = row * d/2 + (col % d)/2 + i
-        const float* ang = p.angles + row * (p.d >> 1) + ((col % p.d) >> 1);
+        float ang[E / 2];
+        load_params<E / 2>(p.angles + row * (p.d >> 1) + ((col % p.d) >> 1), ang);
 #pragma unroll
         for (int j = 0; j < E; j += 2) {
           float sn, cs;
-          sincosf(__ldg(ang + (j >> 1)), &sn, &cs);
+          sincosf(ang[j >> 1], &sn, &cs);
           const float x0 = Chunk<T>::round(f[j]), x1 = Chunk<T>::round(f[j + 1]);  // rope input is the T-cast norm
           f[j] = __fsub_rn(__fmul_rn(x0, cs), __fmul_rn(x1, sn));
           f[j + 1] = __fadd_rn(__fmul_rn(x0, sn), __fmul_rn(x1, cs));
@@ -241,9 +258,11 @@ __global__ void __launch_bounds__(256) gate_residual_kernel(const T* __restrict_
     float xf[8], yf[8];
     Chunk<T>::unpack(xr, xf);
     Chunk<T>::unpack(yr, yf);
+    float gv[8];
+    load_params<8>(gate + col, gv);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float g = Chunk<T>::round(__ldg(gate + col + j));
+      const float g = Chunk<T>::round(gv[j]);
       xf[j] = __fadd_rn(xf[j], Chunk<T>::round(__fmul_rn(yf[j], g)));
     }
     stg_v4(out + e, Chunk<T>::pack(xf));
@@ -259,13 +278,14 @@ __global__ void __launch_bounds__(256) rope_kernel(const T* __restrict__ x, cons
     const int64_t e = c * 8;
     const int64_t row = e / hd;
     const int col = static_cast<int>(e % hd);
-    const float* ang = angles + row * (d >> 1) + ((col % d) >> 1);
+    float ang[4];
+    load_params<4>(angles + row * (d >> 1) + ((col % d) >> 1), ang);
     float f[8];
     Chunk<T>::unpack(ldg_nc_v4(x + e), f);
 #pragma unroll
     for (int j = 0; j < 8; j += 2) {
       float sn, cs;
-      sincosf(__ldg(ang + (j >> 1)), &sn, &cs);
+      sincosf(ang[j >> 1], &sn, &cs);
       const float x0 = f[j], x1 = f[j + 1];
       f[j] = __fsub_rn(__fmul_rn(x0, cs), __fmul_rn(x1, sn));
       f[j + 1] = __fadd_rn(__fmul_rn(x0, sn), __fmul_rn(x1, cs));
@@ -306,9 +326,12 @@ __global__ void __launch_bounds__(256) ln_modulate_quant_tile_kernel(const T* __
   }
   float sc[8], sh[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    sc[j] = col_ok ? __fadd_rn(1.0f, __ldg(scale + col + j)) : 0.f;
-    sh[j] = col_ok ? __ldg(shift + col + j) : 0.f;
+  for (int j = 0; j < 8; ++j) sc[j] = sh[j] = 0.f;
+  if (col_ok) {
+    load_params<8>(scale + col, sc);
+    load_params<8>(shift + col, sh);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sc[j] = __fadd_rn(1.0f, sc[j]);
   }
   float v[8][8];
   float amax = 1e-8f;

@@ -9,7 +9,9 @@
 //   S[2]  TMEM cols [0,128)   int32 128x64 per buffer (double-buffered so Q.K^T of block j+1 overlaps softmax of j)
 //   O     TMEM cols [128,256) fp32 128x128, accumulated by the tensor core across all selected key blocks
 //   After the loop the S columns are reused for the linear-branch product.
-// shared memory (96 KB + LUT, two CTAs per SM): Q int8 16 KB | K int8 2x8 KB | V bf16 2x16 KB | P bf16 2x16 KB.
+// shared memory (104 KB + LUT, two CTAs per SM): Q int8 16 KB | K int8 3x8 KB | V bf16 3x16 KB | P bf16 16 KB.
+//   K and V travel in separate 3-deep TMA rings (K freed right after Q.K^T, V after P.V): the gathered key blocks
+//   are latency-bound L2/HBM reads, so the prefetch distance matters more than anything else.
 //   Q/K/P (and phi(Q), KVW) are K-major 128B-swizzled; V is consumed MN-major straight from its [L, D] rows, so no
 //   transposed/quantised copy of V is ever materialised.
 // The O accumulator is only rescaled when a row maximum grows by more than 2^8 (lazy rescale): P stays <= 256, which
@@ -30,11 +32,12 @@ constexpr uint32_t kQ8Bytes = BLKQ * D;           // 16 KB
 constexpr uint32_t kK8Bytes = BLKK * D;           // 8 KB
 constexpr uint32_t kVBytes = BLKK * D * 2;        // 16 KB (two 64-column blocks of 8 KB)
 constexpr uint32_t kPBytes = BLKQ * BLKK * 2;     // 16 KB
+constexpr int kStages = 3;                        // K and V rings (separate: K is released after Q.K^T, V after P.V)
 constexpr uint32_t kOffQ8 = 0;
 constexpr uint32_t kOffK8 = kOffQ8 + kQ8Bytes;
-constexpr uint32_t kOffV = kOffK8 + 2 * kK8Bytes;
-constexpr uint32_t kOffP = kOffV + 2 * kVBytes;
-constexpr uint32_t kOffBars = kOffP + 2 * kPBytes;  // 96 KB
+constexpr uint32_t kOffV = kOffK8 + kStages * kK8Bytes;
+constexpr uint32_t kOffP = kOffV + kStages * kVBytes;
+constexpr uint32_t kOffBars = kOffP + kPBytes;      // 104 KB
 constexpr uint32_t kBarBytes = 256;
 constexpr uint32_t kOffLut = kOffBars + kBarBytes;
 constexpr uint32_t kTmemCols = 256;
@@ -55,9 +58,9 @@ struct AttnParams {
 };
 
 enum Bar {
-  kBarQFull = 0, kBarKvFull = 1 /*2*/, kBarKvEmpty = 3 /*2*/, kBarSFull = 5 /*2*/, kBarSEmpty = 7 /*2*/,
-  kBarPFull = 9 /*2*/, kBarPEmpty = 11 /*2*/, kBarPvDone = 13, kBarKvwFull = 14, kBarPhiFull = 15, kBarOlFull = 16,
-  kNumBars = 17
+  kBarQFull = 0, kBarKFull = 1 /*3*/, kBarKEmpty = 4 /*3*/, kBarVFull = 7 /*3*/, kBarVEmpty = 10 /*3*/,
+  kBarSFull = 13 /*2*/, kBarSEmpty = 15 /*2*/, kBarPFull = 17, kBarPEmpty = 18, kBarPvDone = 19, kBarKvwFull = 20,
+  kBarPhiFull = 21, kBarOlFull = 22, kNumBars = 23
 };
 
 template <typename T>
@@ -79,14 +82,18 @@ sla_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q8, const __grid_co
 
   if (threadIdx.x == 0) {
     mbar_init(&bars[kBarQFull], 1);
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&bars[kBarKFull + i], 1);
+      mbar_init(&bars[kBarKEmpty + i], 1);
+      mbar_init(&bars[kBarVFull + i], 1);
+      mbar_init(&bars[kBarVEmpty + i], 1);
+    }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&bars[kBarKvFull + i], 1);
-      mbar_init(&bars[kBarKvEmpty + i], 1);
       mbar_init(&bars[kBarSFull + i], 1);
       mbar_init(&bars[kBarSEmpty + i], kSoftmaxWarps);
-      mbar_init(&bars[kBarPFull + i], kSoftmaxWarps);
-      mbar_init(&bars[kBarPEmpty + i], 1);
     }
+    mbar_init(&bars[kBarPFull], kSoftmaxWarps);
+    mbar_init(&bars[kBarPEmpty], 1);
     mbar_init(&bars[kBarPvDone], 1);
     mbar_init(&bars[kBarKvwFull], 1);
     mbar_init(&bars[kBarPhiFull], kSoftmaxWarps);
@@ -118,19 +125,22 @@ sla_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q8, const __grid_co
       mbar_expect_tx(&bars[kBarQFull], kQ8Bytes);
       tma_load_4d(smem + kOffQ8, &tmap_q8, &bars[kBarQFull], 0, m_blk * BLKQ, bh, 0);
       for (int j = 0; j < T_blocks; ++j) {
-        const int st = j & 1;
-        mbar_wait(&bars[kBarKvEmpty + st], ((j >> 1) & 1) ^ 1);
+        const int st = j % kStages;
+        const uint32_t ph = ((j / kStages) & 1) ^ 1;
         const int blk = s_lut[j];
-        mbar_expect_tx(&bars[kBarKvFull + st], kK8Bytes + kVBytes);
-        tma_load_4d(smem + kOffK8 + st * kK8Bytes, &tmap_k8, &bars[kBarKvFull + st], 0, blk * BLKK, bh, 0);
+        mbar_wait(&bars[kBarKEmpty + st], ph);
+        mbar_expect_tx(&bars[kBarKFull + st], kK8Bytes);
+        tma_load_4d(smem + kOffK8 + st * kK8Bytes, &tmap_k8, &bars[kBarKFull + st], 0, blk * BLKK, bh, 0);
+        mbar_wait(&bars[kBarVEmpty + st], ph);
+        mbar_expect_tx(&bars[kBarVFull + st], kVBytes);
         uint8_t* sv = smem + kOffV + st * kVBytes;
-        tma_load_4d(sv, &tmap_v, &bars[kBarKvFull + st], 0, hh, blk * BLKK, b);
-        tma_load_4d(sv + kVBytes / 2, &tmap_v, &bars[kBarKvFull + st], 64, hh, blk * BLKK, b);
+        tma_load_4d(sv, &tmap_v, &bars[kBarVFull + st], 0, hh, blk * BLKK, b);
+        tma_load_4d(sv + kVBytes / 2, &tmap_v, &bars[kBarVFull + st], 64, hh, blk * BLKK, b);
       }
-      // all P.V reads of both V stages must have retired before KVW overwrites them
-      for (int st = 0; st < 2; ++st) {
-        const int uses = (T_blocks - st + 1) / 2;
-        if (uses > 0) mbar_wait(&bars[kBarKvEmpty + st], (uses - 1) & 1);
+      // all P.V reads of the V stages must have retired before KVW overwrites stages 0-1
+      for (int st = 0; st < kStages; ++st) {
+        const int uses = (T_blocks - st + kStages - 1) / kStages;
+        if (uses > 0) mbar_wait(&bars[kBarVEmpty + st], (uses - 1) & 1);
       }
       mbar_expect_tx(&bars[kBarKvwFull], 2 * kVBytes);
       tma_load_4d(smem + kOffV, &tmap_kvw, &bars[kBarKvwFull], 0, 0, bh, 0);             // d_k 0..63  (16 KB)
@@ -151,32 +161,34 @@ sla_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q8, const __grid_co
       const uint64_t qdesc = make_desc_kmajor_sw128(sbase + kOffQ8);
 
       auto issue_pv = [&](int i) {
-        const int sb = i & 1;
-        mbar_wait(&bars[kBarPFull + sb], (i >> 1) & 1);
+        const int st = i % kStages;
+        mbar_wait(&bars[kBarPFull], i & 1);
+        mbar_wait(&bars[kBarVFull + st], (i / kStages) & 1);
         tc_fence_after_sync();
-        const uint64_t pdesc = make_desc_kmajor_sw128(sbase + kOffP + sb * kPBytes);
-        const uint64_t vdesc = make_desc_mnmajor_sw128(sbase + kOffV + sb * kVBytes, kVBytes / 2);
+        const uint64_t pdesc = make_desc_kmajor_sw128(sbase + kOffP);
+        const uint64_t vdesc = make_desc_mnmajor_sw128(sbase + kOffV + st * kVBytes, kVBytes / 2);
 #pragma unroll
         for (int ks = 0; ks < BLKK / 16; ++ks)  // K=16 keys per MMA: P +32 B in its row, V +16 rows (2048 B)
           umma_f16_ss(tmem_base + kColO, pdesc + uint64_t(ks * 2), vdesc + uint64_t(ks * 128), id_pv,
                       (i > 0 || ks > 0) ? 1u : 0u);
-        umma_commit(&bars[kBarKvEmpty + sb]);
-        umma_commit(&bars[kBarPEmpty + sb]);
+        umma_commit(&bars[kBarVEmpty + st]);
+        umma_commit(&bars[kBarPEmpty]);
         umma_commit(&bars[kBarPvDone]);
       };
 
       mbar_wait(&bars[kBarQFull], 0);
       for (int j = 0; j < T_blocks; ++j) {
-        const int st = j & 1;
-        mbar_wait(&bars[kBarKvFull + st], (j >> 1) & 1);
-        mbar_wait(&bars[kBarSEmpty + st], ((j >> 1) & 1) ^ 1);
+        const int st = j % kStages, sb = j & 1;
+        mbar_wait(&bars[kBarKFull + st], (j / kStages) & 1);
+        mbar_wait(&bars[kBarSEmpty + sb], ((j >> 1) & 1) ^ 1);
         tc_fence_after_sync();
         const uint64_t kdesc = make_desc_kmajor_sw128(sbase + kOffK8 + st * kK8Bytes);
 #pragma unroll
         for (int ks = 0; ks < D / 32; ++ks)
-          umma_i8_ss(tmem_base + kColS + st * BLKK, qdesc + uint64_t(ks * 2), kdesc + uint64_t(ks * 2), idesc_qk,
+          umma_i8_ss(tmem_base + kColS + sb * BLKK, qdesc + uint64_t(ks * 2), kdesc + uint64_t(ks * 2), idesc_qk,
                      ks > 0 ? 1u : 0u);
-        umma_commit(&bars[kBarSFull + st]);
+        umma_commit(&bars[kBarSFull + sb]);
+        umma_commit(&bars[kBarKEmpty + st]);
         if (j > 0) issue_pv(j - 1);
       }
       issue_pv(T_blocks - 1);
@@ -187,9 +199,9 @@ sla_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q8, const __grid_co
       tc_fence_after_sync();
 #pragma unroll
       for (int ks = 0; ks < D / 16; ++ks) {
-        const uint32_t off = (ks >> 2) * kPBytes + (ks & 3) * 32;  // 64-wide K chunk, then +32 B per K=16 step
-        const uint64_t adesc = make_desc_kmajor_sw128(sbase + kOffP + off);
-        const uint64_t bdesc = make_desc_kmajor_sw128(sbase + kOffV + off);
+        // 64-wide K chunk (phi: chunk 0 in the P buffer, chunk 1 in the freed Q tile; KVW: V stages 0 and 1), +32 B per K=16 step
+        const uint64_t adesc = make_desc_kmajor_sw128(sbase + ((ks >> 2) ? kOffQ8 : kOffP) + (ks & 3) * 32);
+        const uint64_t bdesc = make_desc_kmajor_sw128(sbase + kOffV + (ks >> 2) * kVBytes + (ks & 3) * 32);
         umma_f16_ss(tmem_base + kColS, adesc, bdesc, id_lin, ks > 0 ? 1u : 0u);
       }
       umma_commit(&bars[kBarOlFull]);
@@ -289,15 +301,15 @@ sla_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q8, const __grid_co
       l_sum += psum;
 
       // ---- P row -> shared memory, K-major SW128: 16-byte chunk c of row r lives at r*128 + ((c ^ (r & 7)) << 4)
-      mbar_wait(&bars[kBarPEmpty + st], ((j >> 1) & 1) ^ 1);
-      uint8_t* prow = sP + st * kPBytes + r * 128;
+      mbar_wait(&bars[kBarPEmpty], (j & 1) ^ 1);     // P.V of block j-1 has finished reading the (single) P buffer
+      uint8_t* prow = sP + r * 128;
 #pragma unroll
       for (int c = 0; c < 8; ++c)
         *reinterpret_cast<uint4*>(prow + ((c ^ (r & 7)) << 4)) =
             make_uint4(pw[4 * c], pw[4 * c + 1], pw[4 * c + 2], pw[4 * c + 3]);
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bars[kBarPFull + st]);
+      if (lane == 0) mbar_arrive(&bars[kBarPFull]);
     }
 
     // ---- linear branch operand: phi(q) = softmax over D of this thread's query row (SLA/core.py:243), rounded to T
@@ -330,12 +342,12 @@ sla_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q8, const __grid_co
         phi[i] = F16Traits<T>::pack(a, c2);
       }
     }
-    // all P.V MMAs retired -> the P buffers may be overwritten with phi(q) (two 64-wide K chunks of 16 KB)
+    // all MMAs retired -> the P buffer and the Q tile may be overwritten with phi(q) (two 64-wide K chunks of 16 KB)
     mbar_wait(&bars[kBarPvDone], (T_blocks - 1) & 1);
     tc_fence_after_sync();
 #pragma unroll
     for (int c = 0; c < 16; ++c) {
-      uint8_t* dst = sP + (c >> 3) * kPBytes + r * 128 + (((c & 7) ^ (r & 7)) << 4);
+      uint8_t* dst = ((c >> 3) ? smem + kOffQ8 : sP) + r * 128 + (((c & 7) ^ (r & 7)) << 4);
       *reinterpret_cast<uint4*>(dst) = make_uint4(phi[4 * c], phi[4 * c + 1], phi[4 * c + 2], phi[4 * c + 3]);
     }
     fence_proxy_async_smem();
