@@ -153,6 +153,10 @@ int tdb200_sla_attn_fwd(const int8_t* q_i8, const float* q_scale, const int8_t* 
 /* Diagnostics: runs a 128x128x64 bf16 tcgen05 MMA with a K-major A and an MN-major B tile staged by TMA and
  * writes the fp32 product to d_out [128,128].  a [128,64] bf16 row-major, b [64,128] bf16 row-major (d = a.b). */
 int tdb200_selftest_umma_bf16(const void* a, const void* b, float* d_out, void* stream);
+/* Diagnostics: TMEM->register read throughput.  One CTA per SM, `warps` (4/8/12/16) warps each issuing `iters`
+ * tcgen05.ld.32x32b.x64 (8 KB per warp instruction), optionally followed by the GEMM's int->float + FMA dequant.
+ * cycles_per_cta [#SMs] receives clock64() deltas. */
+int tdb200_selftest_tmem_read(int warps, int iters, int convert, long long* cycles_per_cta, float* sink, void* stream);
 
 #ifdef __cplusplus
 }

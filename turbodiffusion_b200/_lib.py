@@ -39,6 +39,7 @@ _PROTOS = {
     "tdb200_sla_attn_fwd": [_P, _P, _P, _P, _P, _P, _I, _P, _I64, _P, _P, _P, _P, _I64, _I64, _I64, _I64, _I64, _F,
                             _P],
     "tdb200_selftest_umma_bf16": [_P, _P, _P, _P],
+    "tdb200_selftest_tmem_read": [_I, _I, _I, _P, _P, _P],
 }
 _RESTYPES = {"tdb200_last_error": c_char_p}
 

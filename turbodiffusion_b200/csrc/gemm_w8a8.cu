@@ -13,6 +13,10 @@
 //            int32 partial sums, cvt to fp32 (exact, |sum| < 2^22) and FMA with the block scale into 128 fp32
 //            registers, hand the TMEM buffer back; after the last K-block: round to T, add bias, 16-byte stores.
 //            The dequant of K-block kb overlaps the MMAs of K-block kb+1 (double-buffered TMEM).
+// Measured alternatives (profiles/r01_gemm_experiments.md): 16 dequant warps x 64 columns is ~8% SLOWER; TMA multicast of
+// the B tile inside 2-CTA clusters (kept: -33% L2->SM traffic) is throughput-neutral; a tcgen05.ld probe shows the
+// dequant loop alone runs at 782 clk per K-block (ALU floor 512, I2FP issues on the half-rate ALU pipe), the kernel at
+// ~1100: the remainder is hand-off latency and TMEM port sharing with the MMA's accumulator read-modify-writes.
 // Integer accumulation is exact and the fp32 FMA chain runs in ascending kb order, so the result is bit-identical
 // to the reference restatement (oracle.int8_linear) on the same int8 inputs.
 #include "common.cuh"

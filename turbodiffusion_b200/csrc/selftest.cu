@@ -80,3 +80,65 @@ extern "C" int tdb200_selftest_umma_bf16(const void* a, const void* b, float* d_
   selftest_umma_bf16_kernel<<<1, 128, smem, static_cast<cudaStream_t>(stream)>>>(ta, tb, d_out);
   return check_launch("selftest_umma_bf16_kernel");
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// TMEM -> register read throughput probe: `warps` warps per CTA (one CTA per SM) each issue `iters` tcgen05.ld
+// 32x32b.x64 (8 KB per warp-instruction) back to back; reports cycles per CTA.  Used to decide whether the GEMM's
+// per-K-block dequant is bound by TMEM read bandwidth or by load latency.
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+using namespace tdb;
+template <bool kConvert>
+__global__ void __launch_bounds__(512, 1) tmem_read_probe_kernel(int iters, long long* cycles, float* sink) {
+  __shared__ uint32_t slot;
+  const int warp = threadIdx.x >> 5;
+  if (warp == 0) tmem_alloc<512>(&slot);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t base = slot + (uint32_t((warp & 3) * 32) << 16) + ((warp >> 2) * 64) % 512;
+  float acc[64];
+#pragma unroll
+  for (int j = 0; j < 64; ++j) acc[j] = 0.f;
+  __syncthreads();
+  const long long t0 = clock64();
+  for (int i = 0; i < iters; ++i) {
+    uint32_t r[64];
+    tmem_ld_x64(base, r);
+    tmem_ld_wait();
+    if (kConvert) {
+#pragma unroll
+      for (int j = 0; j < 64; ++j) acc[j] = fmaf(__int2float_rn(static_cast<int>(r[j])), 1.0001f, acc[j]);
+    } else {
+      acc[i & 63] += __uint_as_float(r[i & 63]);
+    }
+  }
+  __syncthreads();
+  const long long t1 = clock64();
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < 64; ++j) s += acc[j];
+  if (s == 123.456f) sink[0] = s;
+  if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after_sync();
+    tmem_dealloc<512>(slot);
+  }
+}
+}  // namespace
+
+extern "C" int tdb200_selftest_tmem_read(int warps, int iters, int convert, long long* cycles_per_cta, float* sink,
+                                         void* stream) {
+  using namespace tdb;
+  if (!cycles_per_cta || !sink || warps < 4 || warps > 16 || warps % 4 != 0)
+    return fail(TDB200_ERR_INVALID_ARG, "selftest_tmem_read: warps must be 4, 8, 12 or 16");
+  if (int rc = require_sm100()) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (convert)
+    tmem_read_probe_kernel<true><<<sm_count(), warps * 32, 0, st>>>(iters, cycles_per_cta, sink);
+  else
+    tmem_read_probe_kernel<false><<<sm_count(), warps * 32, 0, st>>>(iters, cycles_per_cta, sink);
+  return check_launch("tmem_read_probe_kernel");
+}
