@@ -76,6 +76,13 @@ int tdb200_gemm_w8a8(const int8_t* a_q, const float* a_s, const int8_t* b_q, con
 #define TDB200_EPILOGUE_GELU_TANH 1
 int tdb200_gemm_w8a8_ex(const int8_t* a_q, const float* a_s, const int8_t* b_q, const float* b_s, const void* bias,
                         void* c, int c_dtype, int64_t m, int64_t n, int64_t k, int epilogue, void* stream);
+/* GEMM whose output is emitted already block-quantised for the next W8A8 GEMM:
+ *   (out_q, out_s) == tdb200_quant_int8_block128( output of tdb200_gemm_w8a8_ex in dtype `mid_dtype` )   bit for bit,
+ * without the 16-bit tensor ever reaching HBM (FFN: Linear -> GELU -> Int8Linear, ops/core.py:28-57 called twice).
+ * out_q [m,n] int8, out_s [ceil(m/128), n/128] fp32; n % 128 == 0. */
+int tdb200_gemm_w8a8_quant_out(const int8_t* a_q, const float* a_s, const int8_t* b_q, const float* b_s,
+                               const void* bias, int8_t* out_q, float* out_s, int mid_dtype, int64_t m, int64_t n,
+                               int64_t k, int epilogue, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * a3/a4. FastNorm
@@ -149,6 +156,29 @@ int tdb200_sla_attn_fwd(const int8_t* q_i8, const float* q_scale, const int8_t* 
                         const void* v, const void* q, int dtype, const int32_t* lut, int64_t topk, const void* kvw,
                         const float* ksum, const float* proj_b, void* out, int64_t b, int64_t l, int64_t lk,
                         int64_t h, int64_t d, float sm_scale, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a12. LTX-2 (TurboT2AV) prologue variants   (ltx_core/model/transformer/transformer.py:21-94; Triton fast path
+ *      ltx_distillation/fast_norm_kernels.py:388-473).  x, y, residual [b, tokens, n] 16-bit; table [num_ada, n] fp32;
+ *      timestep [b, ts_tokens, num_ada*n] 16-bit with ts_tokens in {1, tokens}; ada value i = table[i] + timestep[.., i, :].
+ *      fp32 math, one rounding to the io dtype.
+ *   modulated_rms_norm_ada:  y = rms_norm(x, eps) * (1 + ada[scale_index]) + ada[shift_index]
+ *   modulate_ada:            y = x * (1 + ada[scale_index]) + ada[shift_index]
+ *   gated_residual_ada:      y = x + residual * ada[gate_index]
+ *   split_rope:              x [b,t,h,d], cos/sin [b,h,t,d/2]:  y[:d/2] = x1*cos - x2*sin,  y[d/2:] = x2*cos + x1*sin
+ *                            (ltx_core/model/transformer/rope.py:42-60)
+ * ------------------------------------------------------------------------------------------- */
+int tdb200_ltx_modulated_rms_norm_ada(const void* x, int dtype, const float* table, const void* timestep, int scale_index,
+                                      int shift_index, int num_ada, void* y, int64_t b, int64_t tokens, int64_t ts_tokens,
+                                      int64_t n, float eps, void* stream);
+int tdb200_ltx_modulate_ada(const void* x, int dtype, const float* table, const void* timestep, int scale_index,
+                            int shift_index, int num_ada, void* y, int64_t b, int64_t tokens, int64_t ts_tokens, int64_t n,
+                            void* stream);
+int tdb200_ltx_gated_residual_ada(const void* x, const void* residual, int dtype, const float* table, const void* timestep,
+                                  int gate_index, int num_ada, void* y, int64_t b, int64_t tokens, int64_t ts_tokens,
+                                  int64_t n, void* stream);
+int tdb200_ltx_split_rope(const void* x, const void* cos_freqs, const void* sin_freqs, int dtype, void* y, int64_t b,
+                          int64_t t, int64_t h, int64_t d, void* stream);
 
 /* Diagnostics: runs a 128x128x64 bf16 tcgen05 MMA with a K-major A and an MN-major B tile staged by TMA and
  * writes the fp32 product to d_out [128,128].  a [128,64] bf16 row-major, b [64,128] bf16 row-major (d = a.b). */

@@ -127,3 +127,26 @@ def test_gemm_linearity_at_full_wan_shape(cuda):
     rows = torch.randint(0, m, (64,), device=cuda)
     ref = (a[rows].float() @ (b1 + b2).float().t())
     assert torch.equal(outs[2][rows], ref)
+
+
+@pytest.mark.parametrize("m,n,k,gelu", [(300, 512, 256, True), (128, 256, 128, False), (1000, 1280, 384, True)])
+def test_gemm_with_fused_quantised_output_is_bit_exact(cuda, m, n, k, gelu):
+    """(q, s) from the fused epilogue == quant_cuda(act(gemm + bias)) of the unfused kernels, and == the oracle."""
+    from turbodiffusion_b200.turbo_diffusion_ops import (gemm_cuda_bias_gelu, gemm_cuda_quant_out, gemm_cuda_swizzle_bias,
+                                                         quant_cuda)
+    x = _mk(m, k, 21 * m + k)
+    w = (_mk(n, k, 23 * n + k, outliers=False).float() * 0.05).to(torch.bfloat16)
+    bias = _mk(1, n, 9, outliers=False)[0]
+    a_q, a_s = O.int8_quant(x)
+    b_q, b_s = O.int8_quant(w)
+    dev = [t.to(cuda) for t in (a_q, a_s, b_q, b_s, bias)]
+    q, s = gemm_cuda_quant_out(*dev, torch.bfloat16, gelu=gelu)
+    c = torch.empty(m, n, dtype=torch.bfloat16, device=cuda)
+    (gemm_cuda_bias_gelu if gelu else gemm_cuda_swizzle_bias)(dev[0], dev[1], dev[2], dev[3], c, dev[4])
+    q2, s2 = quant_cuda(c)
+    torch.cuda.synchronize()
+    assert torch.equal(s, s2) and torch.equal(q, q2)
+    if not gelu:  # the oracle's GELU uses the exact tanh; the plain path is bit-exact end to end
+        y = O.int8_gemm(a_q, a_s, b_q, b_s, torch.bfloat16, bias)
+        q_ref, s_ref = O.int8_quant(y)
+        assert torch.equal(s.cpu(), s_ref) and torch.equal(q.cpu(), q_ref)

@@ -24,6 +24,7 @@ _PROTOS = {
     "tdb200_quant_int8_block128": [_P, _I, _I64, _I64, _P, _P, _P],
     "tdb200_gemm_w8a8": [_P, _P, _P, _P, _P, _P, _I, _I64, _I64, _I64, _P],
     "tdb200_gemm_w8a8_ex": [_P, _P, _P, _P, _P, _P, _I, _I64, _I64, _I64, _I, _P],
+    "tdb200_gemm_w8a8_quant_out": [_P, _P, _P, _P, _P, _P, _P, _I, _I64, _I64, _I64, _I, _P],
     "tdb200_rms_norm_f32": [_P, _P, _P, _I64, _I64, _F, _P],
     "tdb200_layer_norm_f32": [_P, _P, _P, _P, _I64, _I64, _F, _P],
     "tdb200_rms_norm": [_P, _I, _P, _P, _I64, _I64, _F, _P],
@@ -38,6 +39,10 @@ _PROTOS = {
     "tdb200_sla_linear_moments": [_P, _P, _I, _I64, _I64, _I64, _I64, _P, _P, _P],
     "tdb200_sla_attn_fwd": [_P, _P, _P, _P, _P, _P, _I, _P, _I64, _P, _P, _P, _P, _I64, _I64, _I64, _I64, _I64, _F,
                             _P],
+    "tdb200_ltx_modulated_rms_norm_ada": [_P, _I, _P, _P, _I, _I, _I, _P, _I64, _I64, _I64, _I64, _F, _P],
+    "tdb200_ltx_modulate_ada": [_P, _I, _P, _P, _I, _I, _I, _P, _I64, _I64, _I64, _I64, _P],
+    "tdb200_ltx_gated_residual_ada": [_P, _P, _I, _P, _P, _I, _I, _P, _I64, _I64, _I64, _I64, _P],
+    "tdb200_ltx_split_rope": [_P, _P, _P, _I, _P, _I64, _I64, _I64, _I64, _P],
     "tdb200_selftest_umma_bf16": [_P, _P, _P, _P],
     "tdb200_selftest_tmem_read": [_I, _I, _I, _P, _P, _P],
 }

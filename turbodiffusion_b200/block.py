@@ -7,7 +7,7 @@ Per block and per call the reference launches ~60 kernels and re-quantises the s
 here the sequence is
   LN+modulate+quant -> q/k/v GEMMs (shared int8 input) -> RMSNorm+RoPE (q,k) -> SLA (5 launches) -> quant+o GEMM
   -> gate/residual -> LN(affine) -> cross-attention (q/k/v/o GEMMs, library SDPA on 512 keys) -> residual
-  -> LN+modulate+quant -> FFN-up GEMM (+bias+GELU fused) -> quant + FFN-down GEMM -> gate/residual.
+  -> LN+modulate+quant -> FFN-up GEMM (+bias+GELU+block-quant fused, int8 out) -> FFN-down GEMM -> gate/residual.
 Weights use the reference's checkpoint format (Int8Linear buffers `int8_weight`, `scale`, `bias`).
 """
 from __future__ import annotations
@@ -19,7 +19,7 @@ import torch.nn.functional as F
 
 from . import ops
 from .SLA.core import SageSparseLinearAttention
-from .turbo_diffusion_ops import gemm_cuda_bias_gelu, gemm_cuda_swizzle_bias, quant_cuda
+from .turbo_diffusion_ops import gemm_cuda_bias_gelu, gemm_cuda_quant_out, gemm_cuda_swizzle_bias, quant_cuda
 
 LINEARS = ("self_attn.q", "self_attn.k", "self_attn.v", "self_attn.o", "cross_attn.q", "cross_attn.k", "cross_attn.v",
            "cross_attn.o", "ffn.0", "ffn.2")
@@ -106,8 +106,9 @@ class WanBlockB200:
 
         # ---- FFN (:411-413)
         hq, hs = ops.layernorm_modulate_quant(x, e[4], e[3], eps)
-        u = self._gemm(hq, hs, "ffn.0", x.dtype, gelu=True)
-        y = self._linear(u, "ffn.2")
+        # Linear -> GELU(tanh) -> quant for the down projection, all in the up-projection's epilogue
+        uq, us = gemm_cuda_quant_out(hq, hs, sd["ffn.0.int8_weight"], sd["ffn.0.scale"], sd["ffn.0.bias"], x.dtype, gelu=True)
+        y = self._gemm(uq, us, "ffn.2", x.dtype)
         return ops.gate_residual(x, y, e[5])
 
     __call__ = forward

@@ -46,6 +46,8 @@ struct GemmParams {
   int64_t m, n, k;
   int k_blocks, n_tiles, m_tiles, total_tiles;  // total_tiles: tiles, or tile PAIRS in the cluster variant
   int act;  // 0 none, 1 GELU(tanh) applied to the T-rounded (acc [+ bias]) value, result rounded to T again
+  int8_t* out_q;  // when non-NULL: emit quant_int8_block128(T output) instead of the T output itself
+  float* out_s;   // [ceil(m/128), n/128]
 };
 
 // kCluster: CTAs are launched as clusters of 2 that work on vertically adjacent tiles (m, n) and (m+1, n).  Each CTA
@@ -64,6 +66,7 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   uint64_t* tmem_full = bars + 2 * kStages;       // [2]        MMA -> epilogue
   uint64_t* tmem_empty = bars + 2 * kStages + 2;  // [2]        epilogue -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+  float* amax_x = reinterpret_cast<float*>(bars + 2 * kStages + 5);  // [kEpiWarps] block-amax exchange (quantised output)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -208,6 +211,64 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const int64_t row0 = int64_t(m_tile) * BM + q4 * 32;
       const T* bias = static_cast<const T*>(p.bias);
       uint8_t* stage = c_stage + warp * kCStageBytes;
+      if (p.out_q != nullptr) {
+        // ---- fused a1: this thread's 128 values are one row of the 128x128 quant block (m_tile, col0/128).
+        //      y = the T-rounded value the plain epilogue would store; amax over the block; q = sat_s8(rint(y*128/amax)).
+        const bool row_in = row0 + lane < p.m;
+        float amax = 1e-8f;
+#pragma unroll
+        for (int ch = 0; ch < 16; ++ch) {
+          uint32_t bw[4] = {0u, 0u, 0u, 0u};
+          if (bias != nullptr && half_active) {
+            const uint4 b4 = *reinterpret_cast<const uint4*>(bias + col0 + ch * 8);
+            bw[0] = b4.x; bw[1] = b4.y; bw[2] = b4.z; bw[3] = b4.w;
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float y = acc[ch * 8 + j];
+            if (bias != nullptr) y = F16Traits<T>::round(y) + ((j & 1) ? F16Traits<T>::hi(bw[j >> 1]) : F16Traits<T>::lo(bw[j >> 1]));
+            if (act_gelu) y = gelu(F16Traits<T>::round(y));
+            y = (row_in && half_active) ? F16Traits<T>::round(y) : 0.f;
+            acc[ch * 8 + j] = y;
+            amax = fmaxf(amax, fabsf(y));
+          }
+        }
+        amax = warp_max(amax);
+        if (lane == 0) amax_x[warp] = amax;
+        named_bar_sync(1 + half, 128);  // the 4 warps (lane quarters) of this 128-column half
+#pragma unroll
+        for (int w = 0; w < 4; ++w) amax = fmaxf(amax, amax_x[half * 4 + w]);
+        const float r = __fdiv_rn(128.0f, amax);
+        if (q4 == 0 && lane == 0 && half_active && int64_t(m_tile) * BM < p.m)
+          p.out_s[int64_t(m_tile) * (p.n >> 7) + (col0 >> 7)] = amax * 0.0078125f;
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch) {  // 16 int8 per 16-byte chunk
+          uint32_t w[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint32_t word = 0;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+              int qv;
+              asm("cvt.rni.sat.s8.f32 %0, %1;" : "=r"(qv) : "f"(__fmul_rn(acc[ch * 16 + j * 4 + b], r)));
+              word |= (static_cast<uint32_t>(qv) & 0xFFu) << (8 * b);
+            }
+            w[j] = word;
+          }
+          *reinterpret_cast<uint4*>(stage + lane * 128 + ((ch ^ (lane & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rr = 4 * i + (lane >> 3), cc = lane & 7;
+          const uint4 v = *reinterpret_cast<const uint4*>(stage + rr * 128 + ((cc ^ (rr & 7)) << 4));
+          const int64_t grow = row0 + rr;
+          if (half_active && grow < p.m) stg_v4(p.out_q + grow * p.n + col0 + cc * 16, v);
+        }
+        __syncwarp();
+        named_bar_sync(1 + half, 128);  // amax_x is reused by the next tile
+        continue;
+      }
 #pragma unroll
       for (int pass = 0; pass < 2; ++pass) {  // 64 columns per pass
         const int64_t colp = col0 + pass * 64;
@@ -290,9 +351,26 @@ extern "C" int tdb200_gemm_w8a8(const int8_t* a_q, const float* a_s, const int8_
   return tdb200_gemm_w8a8_ex(a_q, a_s, b_q, b_s, bias, c, c_dtype, m, n, k, TDB200_EPILOGUE_NONE, stream);
 }
 
+static int gemm_impl(const int8_t* a_q, const float* a_s, const int8_t* b_q, const float* b_s, const void* bias, void* c,
+                     int8_t* out_q, float* out_s, int c_dtype, int64_t m, int64_t n, int64_t k, int epilogue, void* stream);
+
 extern "C" int tdb200_gemm_w8a8_ex(const int8_t* a_q, const float* a_s, const int8_t* b_q, const float* b_s,
                                    const void* bias, void* c, int c_dtype, int64_t m, int64_t n, int64_t k,
                                    int epilogue, void* stream) {
+  if (!c) return tdb::fail(TDB200_ERR_INVALID_ARG, "gemm_w8a8: null pointer");
+  return gemm_impl(a_q, a_s, b_q, b_s, bias, c, nullptr, nullptr, c_dtype, m, n, k, epilogue, stream);
+}
+
+extern "C" int tdb200_gemm_w8a8_quant_out(const int8_t* a_q, const float* a_s, const int8_t* b_q, const float* b_s,
+                                          const void* bias, int8_t* out_q, float* out_s, int mid_dtype, int64_t m,
+                                          int64_t n, int64_t k, int epilogue, void* stream) {
+  if (!out_q || !out_s) return tdb::fail(TDB200_ERR_INVALID_ARG, "gemm_w8a8_quant_out: null pointer");
+  if (n % 128 != 0) return tdb::fail(TDB200_ERR_UNSUPPORTED, "gemm_w8a8_quant_out: n=%lld must be a multiple of 128", (long long)n);
+  return gemm_impl(a_q, a_s, b_q, b_s, bias, out_q, out_q, out_s, mid_dtype, m, n, k, epilogue, stream);
+}
+
+static int gemm_impl(const int8_t* a_q, const float* a_s, const int8_t* b_q, const float* b_s, const void* bias, void* c,
+                     int8_t* out_q, float* out_s, int c_dtype, int64_t m, int64_t n, int64_t k, int epilogue, void* stream) {
   using namespace tdb;
   if (epilogue != TDB200_EPILOGUE_NONE && epilogue != TDB200_EPILOGUE_GELU_TANH)
     return fail(TDB200_ERR_INVALID_ARG, "gemm_w8a8_ex: unknown epilogue %d", epilogue);
@@ -327,6 +405,8 @@ extern "C" int tdb200_gemm_w8a8_ex(const int8_t* a_q, const float* a_s, const in
   p.n = n;
   p.k = k;
   p.act = epilogue;
+  p.out_q = out_q;
+  p.out_s = out_s;
   p.k_blocks = static_cast<int>(k / BK);
   p.n_tiles = static_cast<int>(cdiv64(n, BN));
   p.m_tiles = static_cast<int>(m_tiles);

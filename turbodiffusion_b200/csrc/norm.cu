@@ -77,6 +77,18 @@ __device__ __forceinline__ void load_params(const float* __restrict__ p, float* 
   }
 }
 
+// sin/cos of a RoPE angle (|x| up to a few thousand rad): two-term Cody-Waite reduction to [-pi, pi] followed by the
+// MUFU approximations (abs error ~2^-21 there).  The reference calls torch.cos/torch.sin (wan2pt1.py:170-171); the
+// difference (< 1e-6 abs) moves a bf16 result by one ulp in ~1e-4 of the elements, inside the stated RoPE tolerance,
+// and keeps this kernel HBM-bound instead of bound by the ~40-instruction accurate sincosf.
+__device__ __forceinline__ void rope_sincos(float x, float* sn, float* cs) {
+  const float n = rintf(x * 0.15915494309189535f);
+  float r = fmaf(n, -6.2831854820251465f, x);
+  r = fmaf(n, 1.7484555e-7f, r);
+  *sn = __sinf(r);
+  *cs = __cosf(r);
+}
+
 enum NormKind { kRms = 0, kLayer = 1 };
 enum PostKind { kPostNone = 0, kPostModulate = 1, kPostRope = 2, kPostStatsOnly = 3 };
 
@@ -200,7 +212,7 @@ __global__ void __launch_bounds__(kThreads) row_norm_kernel(RowParams p) {
 #pragma unroll
         for (int j = 0; j < E; j += 2) {
           float sn, cs;
-          sincosf(ang[j >> 1], &sn, &cs);
+          rope_sincos(ang[j >> 1], &sn, &cs);
           const float x0 = Chunk<T>::round(f[j]), x1 = Chunk<T>::round(f[j + 1]);  // rope input is the T-cast norm
           f[j] = __fsub_rn(__fmul_rn(x0, cs), __fmul_rn(x1, sn));
           f[j + 1] = __fadd_rn(__fmul_rn(x0, sn), __fmul_rn(x1, cs));
@@ -285,7 +297,7 @@ __global__ void __launch_bounds__(256) rope_kernel(const T* __restrict__ x, cons
 #pragma unroll
     for (int j = 0; j < 8; j += 2) {
       float sn, cs;
-      sincosf(ang[j >> 1], &sn, &cs);
+      rope_sincos(ang[j >> 1], &sn, &cs);
       const float x0 = f[j], x1 = f[j + 1];
       f[j] = __fsub_rn(__fmul_rn(x0, cs), __fmul_rn(x1, sn));
       f[j + 1] = __fadd_rn(__fmul_rn(x0, sn), __fmul_rn(x1, cs));

@@ -233,17 +233,20 @@ sla_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q8, const __grid_co
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars[kBarSEmpty + st]);
 
-      // ---- row max on the raw int32 scores (sc > 0), tail columns masked
-      int mx = -2147483647 - 1;
-      if (valid >= BLKK) {
-#pragma unroll
-        for (int c = 0; c < 32; ++c) mx = max(mx, max(static_cast<int>(s0[c]), static_cast<int>(s1[c])));
-      } else {
+      // ---- row max on the raw int32 scores (sc > 0); the ragged last key block (valid < 64) first overwrites its
+      //      masked columns with INT_MIN so the hot path carries no per-element predicates
+      if (valid < BLKK) {
 #pragma unroll
         for (int c = 0; c < 32; ++c) {
-          if (c < valid) mx = max(mx, static_cast<int>(s0[c]));
-          if (c + 32 < valid) mx = max(mx, static_cast<int>(s1[c]));
+          if (c >= valid) s0[c] = 0x80000000u;
+          if (c + 32 >= valid) s1[c] = 0x80000000u;
         }
+      }
+      int mx = -2147483647 - 1;
+#pragma unroll
+      for (int c = 0; c < 32; c += 2) {
+        mx = __vimax3_s32(mx, static_cast<int>(s0[c]), static_cast<int>(s0[c + 1]));
+        mx = __vimax3_s32(mx, static_cast<int>(s1[c]), static_cast<int>(s1[c + 1]));
       }
       const float m_blk_f = static_cast<float>(mx) * sc;
 
@@ -272,31 +275,42 @@ sla_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q8, const __grid_co
         m_used = m_new;
       }
 
-      // ---- P = exp2(s*sc - m_used); int->float via the magic-number add keeps the XU pipe free for ex2
+      // ---- P = exp2(s*sc - m_used); int->float via the magic-number add keeps the XU pipe free for ex2; the scale+bias
+      //      FMA and the row-sum adds run as packed f32x2 instructions.  Masked columns hold INT_MIN (a very negative
+      //      score); their exact removal happens in the ragged-block fix-up below.
       const float cbias = -fmaf(kMagicF, sc, m_used);
-      float psum = 0.f;
+      const float2 sc2 = make_float2(sc, sc), cb2 = make_float2(cbias, cbias);
+      float2 ps2 = make_float2(0.f, 0.f);
       uint32_t pw[32];
 #pragma unroll
       for (int c = 0; c < 32; c += 2) {
-        float p0 = fast_exp2(fmaf(__int_as_float(static_cast<int>(s0[c]) + kMagicI), sc, cbias));
-        float p1 = fast_exp2(fmaf(__int_as_float(static_cast<int>(s0[c + 1]) + kMagicI), sc, cbias));
-        if (valid < BLKK) {
-          p0 = (c < valid) ? p0 : 0.f;
-          p1 = (c + 1 < valid) ? p1 : 0.f;
-        }
-        psum += p0 + p1;
-        pw[c >> 1] = F16Traits<T>::pack(p0, p1);
+        float2 t = __ffma2_rn(make_float2(__int_as_float(static_cast<int>(s0[c]) + kMagicI),
+                                          __int_as_float(static_cast<int>(s0[c + 1]) + kMagicI)), sc2, cb2);
+        t.x = fast_exp2(t.x);
+        t.y = fast_exp2(t.y);
+        ps2 = __fadd2_rn(ps2, t);
+        pw[c >> 1] = F16Traits<T>::pack(t.x, t.y);
       }
 #pragma unroll
       for (int c = 0; c < 32; c += 2) {
-        float p0 = fast_exp2(fmaf(__int_as_float(static_cast<int>(s1[c]) + kMagicI), sc, cbias));
-        float p1 = fast_exp2(fmaf(__int_as_float(static_cast<int>(s1[c + 1]) + kMagicI), sc, cbias));
-        if (valid < BLKK) {
-          p0 = (c + 32 < valid) ? p0 : 0.f;
-          p1 = (c + 33 < valid) ? p1 : 0.f;
+        float2 t = __ffma2_rn(make_float2(__int_as_float(static_cast<int>(s1[c]) + kMagicI),
+                                          __int_as_float(static_cast<int>(s1[c + 1]) + kMagicI)), sc2, cb2);
+        t.x = fast_exp2(t.x);
+        t.y = fast_exp2(t.y);
+        ps2 = __fadd2_rn(ps2, t);
+        pw[16 + (c >> 1)] = F16Traits<T>::pack(t.x, t.y);
+      }
+      float psum = ps2.x + ps2.y;
+      if (valid < BLKK) {
+        // exact fix-up of the ragged block: every masked column produced the same p (same INT_MIN input); remove it
+        // from the row sum and clear its 16-bit slot so the tensor core multiplies V's zero-filled rows by zero
+        const float pm = fast_exp2(fmaf(__int_as_float(static_cast<int>(0x80000000u) + kMagicI), sc, cbias));
+        psum -= static_cast<float>(BLKK - valid) * pm;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          if (2 * i >= valid) pw[i] = 0u;
+          else if (2 * i + 1 >= valid) pw[i] &= 0x0000FFFFu;
         }
-        psum += p0 + p1;
-        pw[16 + (c >> 1)] = F16Traits<T>::pack(p0, p1);
       }
       l_sum += psum;
 

@@ -83,6 +83,20 @@ def gemm_cuda_bias_gelu(a_q, a_s, b_q, b_s, c, bias) -> None:
     _gemm(a_q, a_s, b_q, b_s, c, bias, epilogue=1)
 
 
+def gemm_cuda_quant_out(a_q, a_s, b_q, b_s, bias, mid_dtype, gelu: bool = False):
+    """(q, s) = quant_cuda(act(gemm + bias)) in one kernel; the 16-bit activation never reaches HBM."""
+    require_cuda(a_q, a_s, b_q, b_s, bias)
+    m, n, k = a_q.size(0), b_q.size(0), b_q.size(1)
+    q = torch.empty((m, n), dtype=torch.int8, device=a_q.device)
+    s = torch.empty((_cdiv(m, 128), _cdiv(n, 128)), dtype=torch.float32, device=a_q.device)
+    if bias is not None and bias.dtype != mid_dtype:
+        bias = bias.to(mid_dtype)
+    check(lib().tdb200_gemm_w8a8_quant_out(ptr(a_q), ptr(a_s), ptr(b_q), ptr(b_s), ptr(bias), ptr(q), ptr(s),
+                                           DTYPE_TAG[mid_dtype], m, n, k, 1 if gelu else 0, stream_ptr(a_q.device)),
+          "gemm_cuda_quant_out")
+    return q, s
+
+
 def rms_norm_cuda(x: torch.Tensor, eps: float, w: Optional[torch.Tensor] = None,
                   out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """rmsnorm.cu:57-59: fp32 [M,N] in, fp32 out."""
