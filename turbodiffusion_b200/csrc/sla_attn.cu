@@ -137,14 +137,15 @@ sla_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q8, const __grid_co
         tma_load_4d(sv, &tmap_v, &bars[kBarVFull + st], 0, hh, blk * BLKK, b);
         tma_load_4d(sv + kVBytes / 2, &tmap_v, &bars[kBarVFull + st], 64, hh, blk * BLKK, b);
       }
-      // all P.V reads of the V stages must have retired before KVW overwrites stages 0-1
-      for (int st = 0; st < kStages; ++st) {
+      // KVW (2 x 16 KB K-chunks of the folded moment matrix) goes into the two V stages the LAST key block does not use:
+      // they are released one and two iterations before the loop ends, so this load's latency hides behind the tail.
+      mbar_expect_tx(&bars[kBarKvwFull], 2 * kVBytes);
+      for (int c = 0; c < 2; ++c) {
+        const int st = (T_blocks + c) % kStages;
         const int uses = (T_blocks - st + kStages - 1) / kStages;
         if (uses > 0) mbar_wait(&bars[kBarVEmpty + st], (uses - 1) & 1);
+        tma_load_4d(smem + kOffV + st * kVBytes, &tmap_kvw, &bars[kBarKvwFull], c * 64, 0, bh, 0);  // d_k chunk c
       }
-      mbar_expect_tx(&bars[kBarKvwFull], 2 * kVBytes);
-      tma_load_4d(smem + kOffV, &tmap_kvw, &bars[kBarKvwFull], 0, 0, bh, 0);             // d_k 0..63  (16 KB)
-      tma_load_4d(smem + kOffV + kVBytes, &tmap_kvw, &bars[kBarKvwFull], 64, 0, bh, 0);  // d_k 64..127
     }
   } else if (warp == kMmaWarp) {
     // =============================================================== MMA issuer
@@ -199,9 +200,11 @@ sla_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q8, const __grid_co
       tc_fence_after_sync();
 #pragma unroll
       for (int ks = 0; ks < D / 16; ++ks) {
-        // 64-wide K chunk (phi: chunk 0 in the P buffer, chunk 1 in the freed Q tile; KVW: V stages 0 and 1), +32 B per K=16 step
+        // 64-wide K chunk (phi: chunk 0 in the P buffer, chunk 1 in the freed Q tile; KVW: the two V stages the last
+        // key block did not use), +32 B per K=16 step
         const uint64_t adesc = make_desc_kmajor_sw128(sbase + ((ks >> 2) ? kOffQ8 : kOffP) + (ks & 3) * 32);
-        const uint64_t bdesc = make_desc_kmajor_sw128(sbase + kOffV + (ks >> 2) * kVBytes + (ks & 3) * 32);
+        const uint64_t bdesc =
+            make_desc_kmajor_sw128(sbase + kOffV + ((T_blocks + (ks >> 2)) % kStages) * kVBytes + (ks & 3) * 32);
         umma_f16_ss(tmem_base + kColS, adesc, bdesc, id_lin, ks > 0 ? 1u : 0u);
       }
       umma_commit(&bars[kBarOlFull]);
@@ -242,12 +245,17 @@ sla_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q8, const __grid_co
           if (c + 32 >= valid) s1[c] = 0x80000000u;
         }
       }
-      int mx = -2147483647 - 1;
+      // four independent max chains (depth 8 instead of 32: only two softmax warps share a scheduler, so serial
+      // dependency chains, not issue slots, were the limiter)
+      int mxa = -2147483647 - 1, mxb = mxa, mxc = mxa, mxd = mxa;
 #pragma unroll
-      for (int c = 0; c < 32; c += 2) {
-        mx = __vimax3_s32(mx, static_cast<int>(s0[c]), static_cast<int>(s0[c + 1]));
-        mx = __vimax3_s32(mx, static_cast<int>(s1[c]), static_cast<int>(s1[c + 1]));
+      for (int c = 0; c < 32; c += 4) {
+        mxa = __vimax3_s32(mxa, static_cast<int>(s0[c]), static_cast<int>(s0[c + 1]));
+        mxb = __vimax3_s32(mxb, static_cast<int>(s0[c + 2]), static_cast<int>(s0[c + 3]));
+        mxc = __vimax3_s32(mxc, static_cast<int>(s1[c]), static_cast<int>(s1[c + 1]));
+        mxd = __vimax3_s32(mxd, static_cast<int>(s1[c + 2]), static_cast<int>(s1[c + 3]));
       }
+      const int mx = max(max(mxa, mxb), max(mxc, mxd));
       const float m_blk_f = static_cast<float>(mx) * sc;
 
       // ---- lazy rescale of the O accumulator (warp-uniform decision: tcgen05.ld/st are warp-collective)
@@ -280,26 +288,32 @@ sla_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q8, const __grid_co
       //      score); their exact removal happens in the ragged-block fix-up below.
       const float cbias = -fmaf(kMagicF, sc, m_used);
       const float2 sc2 = make_float2(sc, sc), cb2 = make_float2(cbias, cbias);
-      float2 ps2 = make_float2(0.f, 0.f);
+      float2 psa = make_float2(0.f, 0.f), psb = psa, psc = psa, psd = psa;  // independent row-sum chains
       uint32_t pw[32];
 #pragma unroll
-      for (int c = 0; c < 32; c += 2) {
-        float2 t = __ffma2_rn(make_float2(__int_as_float(static_cast<int>(s0[c]) + kMagicI),
-                                          __int_as_float(static_cast<int>(s0[c + 1]) + kMagicI)), sc2, cb2);
-        t.x = fast_exp2(t.x);
-        t.y = fast_exp2(t.y);
-        ps2 = __fadd2_rn(ps2, t);
-        pw[c >> 1] = F16Traits<T>::pack(t.x, t.y);
+      for (int c = 0; c < 32; c += 4) {
+        float2 t0 = __ffma2_rn(make_float2(__int_as_float(static_cast<int>(s0[c]) + kMagicI),
+                                           __int_as_float(static_cast<int>(s0[c + 1]) + kMagicI)), sc2, cb2);
+        float2 t1 = __ffma2_rn(make_float2(__int_as_float(static_cast<int>(s0[c + 2]) + kMagicI),
+                                           __int_as_float(static_cast<int>(s0[c + 3]) + kMagicI)), sc2, cb2);
+        float2 t2 = __ffma2_rn(make_float2(__int_as_float(static_cast<int>(s1[c]) + kMagicI),
+                                           __int_as_float(static_cast<int>(s1[c + 1]) + kMagicI)), sc2, cb2);
+        float2 t3 = __ffma2_rn(make_float2(__int_as_float(static_cast<int>(s1[c + 2]) + kMagicI),
+                                           __int_as_float(static_cast<int>(s1[c + 3]) + kMagicI)), sc2, cb2);
+        t0.x = fast_exp2(t0.x); t0.y = fast_exp2(t0.y);
+        t1.x = fast_exp2(t1.x); t1.y = fast_exp2(t1.y);
+        t2.x = fast_exp2(t2.x); t2.y = fast_exp2(t2.y);
+        t3.x = fast_exp2(t3.x); t3.y = fast_exp2(t3.y);
+        psa = __fadd2_rn(psa, t0);
+        psb = __fadd2_rn(psb, t1);
+        psc = __fadd2_rn(psc, t2);
+        psd = __fadd2_rn(psd, t3);
+        pw[c >> 1] = F16Traits<T>::pack(t0.x, t0.y);
+        pw[(c >> 1) + 1] = F16Traits<T>::pack(t1.x, t1.y);
+        pw[16 + (c >> 1)] = F16Traits<T>::pack(t2.x, t2.y);
+        pw[17 + (c >> 1)] = F16Traits<T>::pack(t3.x, t3.y);
       }
-#pragma unroll
-      for (int c = 0; c < 32; c += 2) {
-        float2 t = __ffma2_rn(make_float2(__int_as_float(static_cast<int>(s1[c]) + kMagicI),
-                                          __int_as_float(static_cast<int>(s1[c + 1]) + kMagicI)), sc2, cb2);
-        t.x = fast_exp2(t.x);
-        t.y = fast_exp2(t.y);
-        ps2 = __fadd2_rn(ps2, t);
-        pw[16 + (c >> 1)] = F16Traits<T>::pack(t.x, t.y);
-      }
+      const float2 ps2 = __fadd2_rn(__fadd2_rn(psa, psb), __fadd2_rn(psc, psd));
       float psum = ps2.x + ps2.y;
       if (valid < BLKK) {
         // exact fix-up of the ragged block: every masked column produced the same p (same INT_MIN input); remove it
@@ -331,30 +345,44 @@ sla_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q8, const __grid_co
     uint32_t phi[D / 2];  // holds the raw q row first, then phi(q), chunk by chunk in place
     {
       const T* qrow = static_cast<const T*>(p.q) + ((int64_t(b) * p.l + (q_row < p.l ? q_row : p.l - 1)) * p.h + hh) * D;
-      float qmax = -INFINITY;
+      float qm0 = -INFINITY, qm1 = -INFINITY, qm2 = -INFINITY, qm3 = -INFINITY;
 #pragma unroll
       for (int c = 0; c < D / 8; ++c) {
         const uint4 raw = __ldg(reinterpret_cast<const uint4*>(qrow) + c);
         phi[4 * c] = raw.x; phi[4 * c + 1] = raw.y; phi[4 * c + 2] = raw.z; phi[4 * c + 3] = raw.w;
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-          qmax = fmaxf(qmax, fmaxf(F16Traits<T>::lo(phi[4 * c + i]), F16Traits<T>::hi(phi[4 * c + i])));
+        qm0 = fmaxf(qm0, fmaxf(F16Traits<T>::lo(raw.x), F16Traits<T>::hi(raw.x)));
+        qm1 = fmaxf(qm1, fmaxf(F16Traits<T>::lo(raw.y), F16Traits<T>::hi(raw.y)));
+        qm2 = fmaxf(qm2, fmaxf(F16Traits<T>::lo(raw.z), F16Traits<T>::hi(raw.z)));
+        qm3 = fmaxf(qm3, fmaxf(F16Traits<T>::lo(raw.w), F16Traits<T>::hi(raw.w)));
       }
+      const float qmax = fmaxf(fmaxf(qm0, qm1), fmaxf(qm2, qm3));
       const float qoff = qmax * kLog2e;
-      float qsum = 0.f;
+      float qs0 = 0.f, qs1 = 0.f, qs2 = 0.f, qs3 = 0.f;  // independent chains (latency-bound otherwise)
 #pragma unroll
-      for (int i = 0; i < D / 2; ++i)
-        qsum += fast_exp2(fmaf(F16Traits<T>::lo(phi[i]), kLog2e, -qoff)) + fast_exp2(fmaf(F16Traits<T>::hi(phi[i]), kLog2e, -qoff));
-      const float qinv = 1.0f / qsum;
+      for (int i = 0; i < D / 2; i += 2) {
+        qs0 += fast_exp2(fmaf(F16Traits<T>::lo(phi[i]), kLog2e, -qoff));
+        qs1 += fast_exp2(fmaf(F16Traits<T>::hi(phi[i]), kLog2e, -qoff));
+        qs2 += fast_exp2(fmaf(F16Traits<T>::lo(phi[i + 1]), kLog2e, -qoff));
+        qs3 += fast_exp2(fmaf(F16Traits<T>::hi(phi[i + 1]), kLog2e, -qoff));
+      }
+      const float qinv = 1.0f / ((qs0 + qs1) + (qs2 + qs3));
       const float* ks = p.ksum + int64_t(bh) * D;
+      float den1 = 0.f, den2 = 0.f, den3 = 0.f;
 #pragma unroll
-      for (int i = 0; i < D / 2; ++i) {
+      for (int i = 0; i < D / 2; i += 2) {
+        const float4 kv4 = __ldg(reinterpret_cast<const float4*>(ks + 2 * i));
         const float a = F16Traits<T>::round(fast_exp2(fmaf(F16Traits<T>::lo(phi[i]), kLog2e, -qoff)) * qinv);
         const float c2 = F16Traits<T>::round(fast_exp2(fmaf(F16Traits<T>::hi(phi[i]), kLog2e, -qoff)) * qinv);
-        den = fmaf(a, __ldg(ks + 2 * i), den);
-        den = fmaf(c2, __ldg(ks + 2 * i + 1), den);
+        const float a1 = F16Traits<T>::round(fast_exp2(fmaf(F16Traits<T>::lo(phi[i + 1]), kLog2e, -qoff)) * qinv);
+        const float c3 = F16Traits<T>::round(fast_exp2(fmaf(F16Traits<T>::hi(phi[i + 1]), kLog2e, -qoff)) * qinv);
+        den = fmaf(a, kv4.x, den);
+        den1 = fmaf(c2, kv4.y, den1);
+        den2 = fmaf(a1, kv4.z, den2);
+        den3 = fmaf(c3, kv4.w, den3);
         phi[i] = F16Traits<T>::pack(a, c2);
+        phi[i + 1] = F16Traits<T>::pack(a1, c3);
       }
+      den += (den1 + den2) + den3;
     }
     // all MMAs retired -> the P buffer and the Q tile may be overwritten with phi(q) (two 64-wide K chunks of 16 KB)
     mbar_wait(&bars[kBarPvDone], (T_blocks - 1) & 1);
@@ -372,26 +400,45 @@ sla_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q8, const __grid_co
     mbar_wait(&bars[kBarOlFull], 0);
     tc_fence_after_sync();
     const float inv_l = 1.0f / l_sum, inv_den = 1.0f / den;
-    T* orow = static_cast<T*>(p.out) + ((int64_t(b) * p.l + q_row) * p.h + hh) * D;
+    // Staging: rows 0-63 in the P buffer, rows 64-127 in the Q tile (both free once the linear MMA has retired); 256-byte
+    // rows, 16-byte chunk c of row r at (c ^ (r & 15)).  Each warp then writes its own 32 rows, two full rows per
+    // store instruction, instead of one row per lane.
+    uint8_t* stg = (r < 64 ? sP : smem + kOffQ8) + (r & 63) * 256;
 #pragma unroll
     for (int c = 0; c < D / 32; ++c) {
       uint32_t o[32], ol[32];
       tmem_ld_x32(tmem_base + lane_addr + kColO + c * 32, o);
       tmem_ld_x32(tmem_base + lane_addr + kColS + c * 32, ol);
       tmem_ld_wait();
-      if (q_row < p.l) {
+      const float4* pb4 = reinterpret_cast<const float4*>(p.proj_b + c * 32);
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          uint32_t w[4];
+      for (int g = 0; g < 4; ++g) {
+        const float4 b0 = __ldg(pb4 + 2 * g), b1 = __ldg(pb4 + 2 * g + 1);
+        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        uint32_t w[4];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int e = g * 8 + 2 * i;
-            const float y0 = fmaf(__uint_as_float(o[e]), inv_l, fmaf(__uint_as_float(ol[e]), inv_den, __ldg(p.proj_b + c * 32 + e)));
-            const float y1 = fmaf(__uint_as_float(o[e + 1]), inv_l, fmaf(__uint_as_float(ol[e + 1]), inv_den, __ldg(p.proj_b + c * 32 + e + 1)));
-            w[i] = F16Traits<T>::pack(y0, y1);
-          }
-          stg_v4(orow + c * 32 + g * 8, make_uint4(w[0], w[1], w[2], w[3]));
+        for (int i = 0; i < 4; ++i) {
+          const int e = g * 8 + 2 * i;
+          const float y0 = fmaf(__uint_as_float(o[e]), inv_l, fmaf(__uint_as_float(ol[e]), inv_den, bb[2 * i]));
+          const float y1 = fmaf(__uint_as_float(o[e + 1]), inv_l, fmaf(__uint_as_float(ol[e + 1]), inv_den, bb[2 * i + 1]));
+          w[i] = F16Traits<T>::pack(y0, y1);
         }
+        const int ch = c * 4 + g;
+        *reinterpret_cast<uint4*>(stg + ((ch ^ (r & 15)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+    }
+    __syncwarp();
+    {
+      const uint8_t* wbase = (warp < 2 ? sP : smem + kOffQ8) + (warp & 1) * 32 * 256;
+      const int cc = lane & 15;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int rr = 2 * i + (lane >> 4);                       // row within this warp's 32 rows
+        const int rg = (warp & 1) * 32 + rr;                      // row within the 64-row staging region
+        const uint4 v4 = *reinterpret_cast<const uint4*>(wbase + rr * 256 + ((cc ^ (rg & 15)) << 4));
+        const int64_t grow = int64_t(m_blk) * BLKQ + warp * 32 + rr;
+        if (grow < p.l)
+          stg_v4(static_cast<T*>(p.out) + ((int64_t(b) * p.l + grow) * p.h + hh) * D + cc * 8, v4);
       }
     }
     tc_fence_before_sync();

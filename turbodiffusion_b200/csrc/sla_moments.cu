@@ -113,20 +113,27 @@ sla_moments_kernel(const __grid_constant__ CUtensorMap tmap_v, MomParams p) {
       uint32_t w[D / 2];
       if (row < p.l) {
         const uint4* src = reinterpret_cast<const uint4*>(static_cast<const T*>(p.k) + ((int64_t(b) * p.l + row) * p.h + hh) * D);
-        float mx = -INFINITY;
+        float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
 #pragma unroll
         for (int c = 0; c < D / 8; ++c) {
           const uint4 raw = ldg_nc_v4(src + c);
           w[4 * c] = raw.x; w[4 * c + 1] = raw.y; w[4 * c + 2] = raw.z; w[4 * c + 3] = raw.w;
-#pragma unroll
-          for (int q = 0; q < 4; ++q) mx = fmaxf(mx, fmaxf(F16Traits<T>::lo(w[4 * c + q]), F16Traits<T>::hi(w[4 * c + q])));
+          m0 = fmaxf(m0, fmaxf(F16Traits<T>::lo(raw.x), F16Traits<T>::hi(raw.x)));
+          m1 = fmaxf(m1, fmaxf(F16Traits<T>::lo(raw.y), F16Traits<T>::hi(raw.y)));
+          m2 = fmaxf(m2, fmaxf(F16Traits<T>::lo(raw.z), F16Traits<T>::hi(raw.z)));
+          m3 = fmaxf(m3, fmaxf(F16Traits<T>::lo(raw.w), F16Traits<T>::hi(raw.w)));
         }
+        const float mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
         const float off = mx * kLog2e;
-        float sum = 0.f;
+        float sa = 0.f, sb = 0.f, sc4 = 0.f, sd = 0.f;  // independent chains: the row softmax is latency-, not issue-bound
 #pragma unroll
-        for (int q = 0; q < D / 2; ++q)
-          sum += fast_exp2(fmaf(F16Traits<T>::lo(w[q]), kLog2e, -off)) + fast_exp2(fmaf(F16Traits<T>::hi(w[q]), kLog2e, -off));
-        const float inv = 1.0f / sum;
+        for (int q = 0; q < D / 2; q += 2) {
+          sa += fast_exp2(fmaf(F16Traits<T>::lo(w[q]), kLog2e, -off));
+          sb += fast_exp2(fmaf(F16Traits<T>::hi(w[q]), kLog2e, -off));
+          sc4 += fast_exp2(fmaf(F16Traits<T>::lo(w[q + 1]), kLog2e, -off));
+          sd += fast_exp2(fmaf(F16Traits<T>::hi(w[q + 1]), kLog2e, -off));
+        }
+        const float inv = 1.0f / ((sa + sb) + (sc4 + sd));
 #pragma unroll
         for (int q = 0; q < D / 2; ++q)
           w[q] = F16Traits<T>::pack(fast_exp2(fmaf(F16Traits<T>::lo(w[q]), kLog2e, -off)) * inv,
@@ -149,13 +156,17 @@ sla_moments_kernel(const __grid_constant__ CUtensorMap tmap_v, MomParams p) {
       {
         const uint8_t* colbase = sphi + (r >> 6) * kBlockBytes + (r & 7) * 2;
         const int chunk = (r & 63) >> 3;
-        float s = 0.f;
+        float s4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 8
-        for (int rr = 0; rr < kRowsPerTile; ++rr) {
-          const unsigned short raw = *reinterpret_cast<const unsigned short*>(colbase + rr * 128 + ((chunk ^ (rr & 7)) << 4));
-          s += F16Traits<T>::lo(static_cast<uint32_t>(raw));
+        for (int rr = 0; rr < kRowsPerTile; rr += 4) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const unsigned short raw =
+                *reinterpret_cast<const unsigned short*>(colbase + (rr + u) * 128 + ((chunk ^ ((rr + u) & 7)) << 4));
+            s4[u] += F16Traits<T>::lo(static_cast<uint32_t>(raw));
+          }
         }
-        ksum_acc += s;
+        ksum_acc += (s4[0] + s4[1]) + (s4[2] + s4[3]);
       }
     }
     atomicAdd(p.ksum + int64_t(bh) * D + r, ksum_acc);
