@@ -113,6 +113,14 @@ int tdb200_layer_norm_modulate_quant(const void* x, int dtype, const float* scal
                                      float* s, float* row_stats, int64_t m, int64_t n, float eps, void* stream);
 int tdb200_gate_residual(const void* x, const void* y, const float* gate, void* out, int dtype, int64_t m, int64_t n,
                          void* stream);
+/* Cross-kernel fusion of the two above: the gate/residual update (gate == NULL: plain x + y) also emits the row
+ * statistics (mean, rstd incl. the reference's variance padding term) of its OUTPUT, i.e. of the next LayerNorm's input,
+ * and layer_norm_modulate_quant_stats is the tile pass alone, consuming them.  Results are bit-identical to
+ * gate_residual followed by layer_norm_modulate_quant; one full read of the activation per LayerNorm is saved. */
+int tdb200_gate_residual_stats(const void* x, const void* y, const float* gate, void* out, float* row_stats, int dtype,
+                               int64_t m, int64_t n, float eps, void* stream);
+int tdb200_layer_norm_modulate_quant_stats(const void* x, int dtype, const float* row_stats, const float* scale,
+                                           const float* shift, int8_t* q, float* s, int64_t m, int64_t n, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * a6. RoPE, interleaved pairs   (rcm/networks/wan2pt1.py:156-178; flash_attn interleaved=True)

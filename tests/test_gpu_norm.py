@@ -124,3 +124,20 @@ def test_rope_and_fused_rmsnorm_rope(cuda, h, d):
     got2 = ops.rmsnorm_rope(x.reshape(l, h * d).to(cuda), w.to(cuda), ang.to(cuda), 1e-6, h).cpu().reshape(l, h, d)
     frac, worst = _ulp_report(got2, ref2)
     assert worst <= 1.0 and frac < 5e-3, (frac, worst)
+
+
+@pytest.mark.parametrize("m,n,gated", [(300, 1536, True), (131, 5120, False)])
+def test_residual_with_fused_stats_equals_the_two_pass_path(cuda, m, n, gated):
+    """gate_residual_stats + layernorm_modulate_quant_from_stats == gate_residual + layernorm_modulate_quant, bit for bit."""
+    import turbodiffusion_b200.ops as ops
+    x, y = _x(m, n, 1).to(cuda), _x(m, n, 2).to(cuda)
+    g = torch.Generator().manual_seed(3)
+    gate = torch.randn(n, generator=g).to(cuda) if gated else None
+    scale, shift = (torch.randn(n, generator=g) * 0.1).to(cuda), (torch.randn(n, generator=g) * 0.1).to(cuda)
+    out_a = ops.gate_residual(x, y, gate) if gated else x + y
+    q_a, s_a = ops.layernorm_modulate_quant(out_a, scale, shift, 1e-6)
+    out_b, stats = ops.gate_residual_stats(x, y, gate, 1e-6)
+    q_b, s_b = ops.layernorm_modulate_quant_from_stats(out_b, stats, scale, shift)
+    torch.cuda.synchronize()
+    assert torch.equal(out_a.view(torch.int16), out_b.view(torch.int16))
+    assert torch.equal(s_a, s_b) and torch.equal(q_a, q_b)

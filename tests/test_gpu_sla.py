@@ -176,3 +176,48 @@ def test_sla_forward_vs_reference_golden(cuda, name):
     out = mod(g["q"].to(cuda), g["k"].to(cuda), g["v"].to(cuda)).cpu()
     s = O.stats(out, g["out"])
     assert s["cos"] >= 0.999 and s["rel_l2"] <= 2e-2, s
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_sage_sla_forward_head_dim_64_and_fp16(cuda, dtype):
+    """SageSLA accepts head_dim 64 (SLA/core.py:207) and use_bf16=False (fp16 compute, SLA/core.py:136)."""
+    from turbodiffusion_b200.SLA import SageSparseLinearAttention
+    from turbodiffusion_b200.SLA.utils import block_map_from_pools, quant_qk
+    b, l, h, d, ratio = 2, 333, 2, 64, 0.5
+    q, k, v = _qkv(b, l, h, d, 77, dtype=dtype)
+    g = torch.Generator().manual_seed(5)
+    mod = SageSparseLinearAttention(d, ratio, use_bf16=(dtype == torch.bfloat16)).to(cuda)
+    with torch.no_grad():
+        mod.proj_l.weight.copy_(torch.randn(d, d, generator=g) * 0.05)
+        mod.proj_l.bias.copy_(torch.randn(d, generator=g) * 0.05)
+    out = mod(q.to(cuda), k.to(cuda), v.to(cuda)).cpu()
+    assert out.shape == q.shape and out.dtype == dtype
+    import torch.nn.functional as F
+    prep = quant_qk(F.pad(q, (0, 64)).to(cuda).contiguous(), F.pad(k, (0, 64)).to(cuda).contiguous())
+    topk = min(prep.nblk, int(ratio * prep.nblk))
+    _, lut = block_map_from_pools(prep.q_pool, prep.k_pool, topk)
+    w, bias = mod.proj_l.weight.detach().cpu(), mod.proj_l.bias.detach().cpu()
+    exact = O.sla_forward(q, k, v, w, bias, ratio, mode="exact", lut=lut.cpu(), dtype=dtype)
+    s = O.stats(out, exact)
+    assert s["cos"] >= 0.999 and s["rel_l2"] <= 2e-2, s
+
+
+def test_sla_forward_vs_reference_golden_d64(cuda):
+    from turbodiffusion_b200.SLA import SparseLinearAttention
+    g = torch.load(os.path.join(GOLD, "sla_b.pt"))
+    mod = SparseLinearAttention(64, g["topk_ratio"], BLKQ=128, BLKK=64).to(cuda)
+    with torch.no_grad():
+        mod.proj_l.weight.copy_(g["proj_w"])
+        mod.proj_l.bias.copy_(g["proj_b"])
+    out = mod(g["q"].to(cuda), g["k"].to(cuda), g["v"].to(cuda)).cpu()
+    s = O.stats(out, g["out"])
+    assert s["cos"] >= 0.999 and s["rel_l2"] <= 2e-2, s
+
+
+def test_fp16_block_map_and_quant(cuda):
+    from turbodiffusion_b200.SLA.utils import quant_qk
+    q, k, _ = _qkv(1, 600, 2, 128, 3, dtype=torch.float16)
+    prep = quant_qk(q.to(cuda), k.to(cuda))
+    qh = q.transpose(1, 2).contiguous()
+    q_i8, q_s = O.sage_quant_blocks(qh, 128)
+    assert torch.equal(prep.q_scale.cpu(), q_s) and torch.equal(prep.q_i8.cpu(), q_i8)

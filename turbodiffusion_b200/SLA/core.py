@@ -59,23 +59,47 @@ class _SLABase(nn.Module):
             nn.init.zeros_(self.proj_l.bias)
 
     def forward(self, q, k, v, return_sparsity=False):
-        """q,k,v [B, L, H, D] (any float dtype) -> [B, L, H, D] in q.dtype."""
+        """q,k,v [B, L, H, D] (any float dtype), D in {64, 128} (SLA/core.py:207) -> [B, L, H, D] in q.dtype."""
         require_cuda(q, k, v)
         dtype = q.dtype
         q, k, v = (t.to(self.dtype).contiguous() for t in (q, k, v))
         b, l, h, d = q.shape
+        if d == 64:
+            return self._forward_d64(q, k, v, dtype, return_sparsity)
+        if d != 128:
+            raise AssertionError("headdim should be in [64, 128].")  # SLA/core.py:207
+        o, ratio = self._forward_d128(q, k, v, q, k, d ** -0.5, self.proj_l.weight, self.proj_l.bias)
+        o = o.to(dtype)
+        return (o, ratio) if return_sparsity else o
+
+    def _forward_d128(self, q, k, v, q_feat, k_feat, sm_scale, proj_w, proj_b):
+        """q,k,v: tensors the sparse branch sees; q_feat,k_feat: tensors the softmax feature map sees (they differ only for
+        padded 64-wide heads)."""
         prep = quant_qk(q, k)
         nblk = prep.nblk
         real_topk = min(nblk, int(self.topk * nblk))
         sparse_map, lut = block_map_from_pools(prep.q_pool, prep.k_pool, real_topk)
-        kv, ksum = linear_moments(k, v)
+        kv, ksum = linear_moments(k_feat, v)
         # proj_l folded into the moments: (phi(q) KV / den) W^T + b == phi(q) (W KV^T)^T / den + b ; kv is [dv, dk]
-        kvw = torch.matmul(self.proj_l.weight.float(), kv).to(self.dtype).contiguous()  # [B,H,d_out,d_k]
-        o = attn_fwd(prep, v, q, lut, real_topk, kvw, ksum, self.proj_l.bias.float().contiguous(), d ** -0.5)
-        o = o.to(dtype)
-        if return_sparsity:
-            return o, real_topk / nblk
-        return o
+        kvw = torch.matmul(proj_w.float(), kv).to(self.dtype).contiguous()  # [B,H,d_out,d_k]
+        o = attn_fwd(prep, v, q_feat, lut, real_topk, kvw, ksum, proj_b.float().contiguous(), sm_scale)
+        return o, real_topk / nblk
+
+    def _forward_d64(self, q, k, v, dtype, return_sparsity):
+        """64-wide heads run through the 128-wide kernels: q/k/v are zero-padded (scores, pooled scores, Sage scales and
+        P.V are unchanged by zero channels), while the tensors feeding softmax-over-D are padded with a large negative value
+        so the padded channels get phi = 0; proj_l is embedded in the top-left 64x64 corner.  (Native 64-wide tiles: next.)"""
+        pad = (0, 64)
+        qz, kz, vz = (F.pad(t, pad) for t in (q, k, v))
+        qf, kf = F.pad(q, pad, value=-3.0e4), F.pad(k, pad, value=-3.0e4)
+        w = torch.zeros(128, 128, dtype=torch.float32, device=q.device)
+        w[:64, :64] = self.proj_l.weight.float()
+        bias = torch.zeros(128, dtype=torch.float32, device=q.device)
+        bias[:64] = self.proj_l.bias.float()
+        o, ratio = self._forward_d128(qz.contiguous(), kz.contiguous(), vz.contiguous(), qf.contiguous(), kf.contiguous(),
+                                      64 ** -0.5, w, bias)
+        o = o[..., :64].contiguous().to(dtype)
+        return (o, ratio) if return_sparsity else o
 
 
 class SparseLinearAttention(_SLABase):

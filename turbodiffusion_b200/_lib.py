@@ -32,6 +32,8 @@ _PROTOS = {
     "tdb200_layer_norm_modulate": [_P, _I, _P, _P, _P, _I64, _I64, _F, _P],
     "tdb200_layer_norm_modulate_quant": [_P, _I, _P, _P, _P, _P, _P, _I64, _I64, _F, _P],
     "tdb200_gate_residual": [_P, _P, _P, _P, _I, _I64, _I64, _P],
+    "tdb200_gate_residual_stats": [_P, _P, _P, _P, _P, _I, _I64, _I64, _F, _P],
+    "tdb200_layer_norm_modulate_quant_stats": [_P, _I, _P, _P, _P, _P, _P, _I64, _I64, _P],
     "tdb200_rope_interleaved": [_P, _I, _P, _P, _I64, _I64, _I64, _P],
     "tdb200_rms_norm_rope": [_P, _I, _P, _P, _P, _I64, _I64, _I64, _F, _P],
     "tdb200_sla_quant_qk": [_P, _P, _I, _I64, _I64, _I64, _I64, _I64, _P, _P, _P, _P, _P, _P, _P, _P],

@@ -75,14 +75,20 @@ class WanBlockB200:
         return self._gemm(xq, xs, name, x.dtype, gelu)
 
     # -- forward -------------------------------------------------------------------------------------------------
-    def forward(self, x: torch.Tensor, e0: torch.Tensor, angles: torch.Tensor, context: torch.Tensor) -> torch.Tensor:
-        """x [L, dim] 16-bit, e0 [6, dim] fp32 (time modulation), angles [L, head_dim/2] fp32, context [Lc, dim]."""
+    def forward(self, x: torch.Tensor, e0: torch.Tensor, angles: torch.Tensor, context: torch.Tensor,
+                stats: Optional[torch.Tensor] = None, want_stats: bool = False):
+        """x [L, dim] 16-bit, e0 [6, dim] fp32 (time modulation), angles [L, head_dim/2] fp32, context [Lc, dim].
+        `stats`: LayerNorm row statistics of x if the producer of x already computed them (the previous block's last
+        residual kernel does); with want_stats=True returns (x_out, stats_of_x_out) for the next block."""
         sd, dim, h, d, eps = self.sd, self.dim, self.heads, self.head_dim, self.eps
         l = x.shape[0]
         e = (sd["modulation"][0] + e0).contiguous()  # [6, dim] fp32 (wan2pt1.py:400)
 
         # ---- self-attention (wan2pt1.py:404, 251-274)
-        xq, xs = ops.layernorm_modulate_quant(x, e[1], e[0], eps)
+        if stats is None:
+            xq, xs = ops.layernorm_modulate_quant(x, e[1], e[0], eps)
+        else:
+            xq, xs = ops.layernorm_modulate_quant_from_stats(x, stats, e[1], e[0])
         q = self._gemm(xq, xs, "self_attn.q", x.dtype)
         k = self._gemm(xq, xs, "self_attn.k", x.dtype)
         v = self._gemm(xq, xs, "self_attn.v", x.dtype)
@@ -102,13 +108,16 @@ class WanBlockB200:
         ca = F.scaled_dot_product_attention(cq.view(1, l, h, d).transpose(1, 2), ck.view(1, lc, h, d).transpose(1, 2),
                                             cv.view(1, lc, h, d).transpose(1, 2))
         ca = ca.transpose(1, 2).reshape(l, dim)
-        x = x + self._linear(ca, "cross_attn.o")
+        # x + cross_attn(...) and, in the same pass, the row statistics the FFN's LayerNorm needs
+        x, st2 = ops.gate_residual_stats(x, self._linear(ca, "cross_attn.o"), None, eps)
 
         # ---- FFN (:411-413)
-        hq, hs = ops.layernorm_modulate_quant(x, e[4], e[3], eps)
+        hq, hs = ops.layernorm_modulate_quant_from_stats(x, st2, e[4], e[3])
         # Linear -> GELU(tanh) -> quant for the down projection, all in the up-projection's epilogue
         uq, us = gemm_cuda_quant_out(hq, hs, sd["ffn.0.int8_weight"], sd["ffn.0.scale"], sd["ffn.0.bias"], x.dtype, gelu=True)
         y = self._gemm(uq, us, "ffn.2", x.dtype)
+        if want_stats:
+            return ops.gate_residual_stats(x, y, e[5], eps)
         return ops.gate_residual(x, y, e[5])
 
     __call__ = forward
@@ -124,6 +133,11 @@ class WanHotPath:
                        for i in range(num_layers)]
 
     def step(self, x, e0, angles, context):
-        for blk in self.blocks:
-            x = blk(x, e0, angles, context)
+        stats = None
+        last = len(self.blocks) - 1
+        for i, blk in enumerate(self.blocks):
+            if i < last:  # the block's final residual kernel also emits the next block's LayerNorm statistics
+                x, stats = blk(x, e0, angles, context, stats, want_stats=True)
+            else:
+                x = blk(x, e0, angles, context, stats)
         return x

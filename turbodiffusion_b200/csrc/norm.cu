@@ -105,10 +105,12 @@ struct RowParams {
   int n;
   int d;                // head dim for RoPE
   float eps;
+  const void* res_y;    // kResidIn: x <- T(x + T(res_y * T(gate)))  (gate NULL: plain x + res_y), written to `y` first
+  const float* gate;
 };
 
 // T: element type of x and y.  kChunks: 16-byte chunks per thread.
-template <typename T, int kNorm, int kPost, int kThreads, int kChunks>
+template <typename T, int kNorm, int kPost, int kThreads, int kChunks, bool kResidIn = false>
 __global__ void __launch_bounds__(kThreads) row_norm_kernel(RowParams p) {
   __shared__ float red[kThreads / 32];
   constexpr int E = Chunk<T>::kElems;
@@ -122,6 +124,28 @@ __global__ void __launch_bounds__(kThreads) row_norm_kernel(RowParams p) {
     const int c = threadIdx.x + i * kThreads;
     raw[i] = make_uint4(0u, 0u, 0u, 0u);
     if (c < nchunks) raw[i] = ldg_nc_v4(xr + c * E);
+  }
+  if (kResidIn) {
+    // fused gate/residual update (wan2pt1.py:405-406): the updated row is stored and becomes the LayerNorm input
+    const T* yr_in = static_cast<const T*>(p.res_y) + row * p.n;
+    T* out = static_cast<T*>(p.y) + row * p.n;
+#pragma unroll
+    for (int i = 0; i < kChunks; ++i) {
+      const int c = threadIdx.x + i * kThreads;
+      if (c < nchunks) {
+        float xf[E], yf[E], gv[E];
+        Chunk<T>::unpack(raw[i], xf);
+        Chunk<T>::unpack(ldg_nc_v4(yr_in + c * E), yf);
+        if (p.gate != nullptr) load_params<E>(p.gate + c * E, gv);
+#pragma unroll
+        for (int j = 0; j < E; ++j) {
+          const float t = (p.gate != nullptr) ? Chunk<T>::round(__fmul_rn(yf[j], Chunk<T>::round(gv[j]))) : yf[j];
+          xf[j] = __fadd_rn(xf[j], t);
+        }
+        raw[i] = Chunk<T>::pack(xf);  // rounded to T: exactly what a separate LayerNorm pass would read back
+        stg_v4(out + c * E, raw[i]);
+      }
+    }
   }
 
   const float inv_n = 1.0f / static_cast<float>(p.n);
@@ -223,14 +247,14 @@ __global__ void __launch_bounds__(kThreads) row_norm_kernel(RowParams p) {
   }
 }
 
-template <typename T, int kNorm, int kPost>
+template <typename T, int kNorm, int kPost, bool kResidIn = false>
 int launch_rows(const RowParams& p, cudaStream_t st) {
   constexpr int E = Chunk<T>::kElems;
   const int nchunks = p.n / E;
   if (p.m > 0x7FFFFFFFll) return fail(TDB200_ERR_UNSUPPORTED, "row kernel: too many rows");
   const unsigned grid = static_cast<unsigned>(p.m);
 #define TDB_LAUNCH(TH, CH)                                                         \
-  row_norm_kernel<T, kNorm, kPost, TH, CH><<<grid, TH, 0, st>>>(p);                \
+  row_norm_kernel<T, kNorm, kPost, TH, CH, kResidIn><<<grid, TH, 0, st>>>(p);      \
   return check_launch("row_norm_kernel")
   if (nchunks <= 128) { TDB_LAUNCH(128, 1); }
   if (nchunks <= 256) { TDB_LAUNCH(128, 2); }
@@ -397,7 +421,7 @@ extern "C" int tdb200_rms_norm_f32(const float* x, const float* w, float* y, int
                                    void* stream) {
   if (int rc = check_rows("rms_norm_f32", x, y, m, n, 4)) return rc;
   if (m == 0) return TDB200_OK;
-  RowParams p{x, y, w, nullptr, nullptr, nullptr, nullptr, nullptr, m, static_cast<int>(n), 0, eps};
+  RowParams p{x, y, w, nullptr, nullptr, nullptr, nullptr, nullptr, m, static_cast<int>(n), 0, eps, nullptr, nullptr};
   return launch_rows<float, kRms, kPostNone>(p, static_cast<cudaStream_t>(stream));
 }
 
@@ -405,7 +429,7 @@ extern "C" int tdb200_layer_norm_f32(const float* x, const float* w, const float
                                      float eps, void* stream) {
   if (int rc = check_rows("layer_norm_f32", x, y, m, n, 4)) return rc;
   if (m == 0) return TDB200_OK;
-  RowParams p{x, y, w, b, nullptr, nullptr, nullptr, nullptr, m, static_cast<int>(n), 0, eps};
+  RowParams p{x, y, w, b, nullptr, nullptr, nullptr, nullptr, m, static_cast<int>(n), 0, eps, nullptr, nullptr};
   return launch_rows<float, kLayer, kPostNone>(p, static_cast<cudaStream_t>(stream));
 }
 
@@ -413,7 +437,7 @@ extern "C" int tdb200_rms_norm(const void* x, int dtype, const float* w, void* y
                                void* stream) {
   if (int rc = check_rows("rms_norm", x, y, m, n, 8)) return rc;
   if (m == 0) return TDB200_OK;
-  RowParams p{x, y, w, nullptr, nullptr, nullptr, nullptr, nullptr, m, static_cast<int>(n), 0, eps};
+  RowParams p{x, y, w, nullptr, nullptr, nullptr, nullptr, nullptr, m, static_cast<int>(n), 0, eps, nullptr, nullptr};
   return dispatch16<kRms, kPostNone>(dtype, p, static_cast<cudaStream_t>(stream), "rms_norm");
 }
 
@@ -421,7 +445,7 @@ extern "C" int tdb200_layer_norm(const void* x, int dtype, const float* w, const
                                  int64_t n, float eps, void* stream) {
   if (int rc = check_rows("layer_norm", x, y, m, n, 8)) return rc;
   if (m == 0) return TDB200_OK;
-  RowParams p{x, y, w, b, nullptr, nullptr, nullptr, nullptr, m, static_cast<int>(n), 0, eps};
+  RowParams p{x, y, w, b, nullptr, nullptr, nullptr, nullptr, m, static_cast<int>(n), 0, eps, nullptr, nullptr};
   return dispatch16<kLayer, kPostNone>(dtype, p, static_cast<cudaStream_t>(stream), "layer_norm");
 }
 
@@ -430,7 +454,7 @@ extern "C" int tdb200_layer_norm_modulate(const void* x, int dtype, const float*
   if (int rc = check_rows("layer_norm_modulate", x, y, m, n, 8)) return rc;
   if (!scale || !shift) return tdb::fail(TDB200_ERR_INVALID_ARG, "layer_norm_modulate: null scale/shift");
   if (m == 0) return TDB200_OK;
-  RowParams p{x, y, nullptr, nullptr, scale, shift, nullptr, nullptr, m, static_cast<int>(n), 0, eps};
+  RowParams p{x, y, nullptr, nullptr, scale, shift, nullptr, nullptr, m, static_cast<int>(n), 0, eps, nullptr, nullptr};
   return dispatch16<kLayer, kPostModulate>(dtype, p, static_cast<cudaStream_t>(stream), "layer_norm_modulate");
 }
 
@@ -443,7 +467,7 @@ extern "C" int tdb200_layer_norm_modulate_quant(const void* x, int dtype, const 
     return fail(TDB200_ERR_INVALID_ARG, "layer_norm_modulate_quant: null pointer");
   if (m == 0) return TDB200_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  RowParams p{x, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, row_stats, m, static_cast<int>(n), 0, eps};
+  RowParams p{x, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, row_stats, m, static_cast<int>(n), 0, eps, nullptr, nullptr};
   if (int rc = dispatch16<kLayer, kPostStatsOnly>(dtype, p, st, "layer_norm_modulate_quant(stats)")) return rc;
   const int64_t nb = cdiv64(n, 128), mb = cdiv64(m, 128);
   if (mb > 65535) return fail(TDB200_ERR_UNSUPPORTED, "layer_norm_modulate_quant: m too large");
@@ -505,6 +529,42 @@ extern "C" int tdb200_rms_norm_rope(const void* x, int dtype, const float* w, co
   if (int rc = check_rows("rms_norm_rope", x, y, l, h * d, 8)) return rc;
   if (!angles || !w || d % 8 != 0) return fail(TDB200_ERR_INVALID_ARG, "rms_norm_rope: null pointer or d %% 8 != 0");
   if (l == 0) return TDB200_OK;
-  RowParams p{x, y, w, nullptr, nullptr, nullptr, angles, nullptr, l, static_cast<int>(h * d), static_cast<int>(d), eps};
+  RowParams p{x, y, w, nullptr, nullptr, nullptr, angles, nullptr, l, static_cast<int>(h * d), static_cast<int>(d), eps, nullptr, nullptr};
   return dispatch16<kRms, kPostRope>(dtype, p, static_cast<cudaStream_t>(stream), "rms_norm_rope");
+}
+
+extern "C" int tdb200_gate_residual_stats(const void* x, const void* y, const float* gate, void* out, float* row_stats,
+                                          int dtype, int64_t m, int64_t n, float eps, void* stream) {
+  using namespace tdb;
+  if (int rc = check_rows("gate_residual_stats", x, out, m, n, 8)) return rc;
+  if (!y || !row_stats || !aligned16(y)) return fail(TDB200_ERR_INVALID_ARG, "gate_residual_stats: bad y/stats pointer");
+  if (m == 0) return TDB200_OK;
+  RowParams p{x, out, nullptr, nullptr, nullptr, nullptr, nullptr, row_stats, m, static_cast<int>(n), 0, eps, y, gate};
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == TDB200_DTYPE_BF16) return launch_rows<__nv_bfloat16, kLayer, kPostStatsOnly, true>(p, st);
+  if (dtype == TDB200_DTYPE_FP16) return launch_rows<__half, kLayer, kPostStatsOnly, true>(p, st);
+  return fail(TDB200_ERR_UNSUPPORTED, "gate_residual_stats: dtype tag %d", dtype);
+}
+
+extern "C" int tdb200_layer_norm_modulate_quant_stats(const void* x, int dtype, const float* row_stats, const float* scale,
+                                                      const float* shift, int8_t* q, float* s, int64_t m, int64_t n,
+                                                      void* stream) {
+  using namespace tdb;
+  if (int rc = check_rows("layer_norm_modulate_quant_stats", x, q, m, n, 8)) return rc;
+  if (!scale || !shift || !s || !row_stats)
+    return fail(TDB200_ERR_INVALID_ARG, "layer_norm_modulate_quant_stats: null pointer");
+  if (m == 0) return TDB200_OK;
+  const int64_t nb = cdiv64(n, 128), mb = cdiv64(m, 128);
+  if (mb > 65535) return fail(TDB200_ERR_UNSUPPORTED, "layer_norm_modulate_quant_stats: m too large");
+  dim3 grid(static_cast<unsigned>(nb), static_cast<unsigned>(mb));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == TDB200_DTYPE_BF16)
+    ln_modulate_quant_tile_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), row_stats,
+                                                                      scale, shift, q, s, m, n, static_cast<int>(nb));
+  else if (dtype == TDB200_DTYPE_FP16)
+    ln_modulate_quant_tile_kernel<__half><<<grid, 256, 0, st>>>(static_cast<const __half*>(x), row_stats, scale, shift,
+                                                               q, s, m, n, static_cast<int>(nb));
+  else
+    return fail(TDB200_ERR_UNSUPPORTED, "layer_norm_modulate_quant_stats: dtype tag %d", dtype);
+  return check_launch("ln_modulate_quant_tile_kernel");
 }

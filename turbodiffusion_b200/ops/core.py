@@ -246,6 +246,28 @@ def gate_residual(x: torch.Tensor, y: torch.Tensor, gate: torch.Tensor) -> torch
     return out.reshape(x.shape)
 
 
+def gate_residual_stats(x: torch.Tensor, y: torch.Tensor, gate: Optional[torch.Tensor], eps: float):
+    """(x + y * gate.type_as(x)  [gate None: x + y],  row statistics of that result for the next LayerNorm)."""
+    x2, y2 = _rows16(x), _rows16(y)
+    out = torch.empty_like(x2)
+    stats = torch.empty((2 * x2.shape[0],), dtype=torch.float32, device=x.device)
+    check(lib().tdb200_gate_residual_stats(ptr(x2), ptr(y2), ptr(gate), ptr(out), ptr(stats), DTYPE_TAG[x.dtype],
+                                           x2.shape[0], x2.shape[1], float(eps), stream_ptr(x.device)), "gate_residual_stats")
+    return out.reshape(x.shape), stats
+
+
+def layernorm_modulate_quant_from_stats(x: torch.Tensor, stats: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor):
+    """The tile pass of layernorm_modulate_quant with precomputed row statistics (from gate_residual_stats)."""
+    x2 = _rows16(x)
+    m, n = x2.shape
+    q = torch.empty((m, n), dtype=torch.int8, device=x.device)
+    s = torch.empty((cdiv(m, 128), cdiv(n, 128)), dtype=torch.float32, device=x.device)
+    check(lib().tdb200_layer_norm_modulate_quant_stats(ptr(x2), DTYPE_TAG[x.dtype], ptr(stats), ptr(scale), ptr(shift),
+                                                       ptr(q), ptr(s), m, n, stream_ptr(x.device)),
+          "layernorm_modulate_quant_from_stats")
+    return q, s
+
+
 def rope_interleaved(x: torch.Tensor, angles: torch.Tensor) -> torch.Tensor:
     """rope_apply (wan2pt1.py:156-178).  x [..., L, H, D] with leading batch folded into L by the caller; angles [L, D/2]."""
     require_cuda(x, angles)
