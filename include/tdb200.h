@@ -191,6 +191,9 @@ int tdb200_ltx_split_rope(const void* x, const void* cos_freqs, const void* sin_
 /* Diagnostics: runs a 128x128x64 bf16 tcgen05 MMA with a K-major A and an MN-major B tile staged by TMA and
  * writes the fp32 product to d_out [128,128].  a [128,64] bf16 row-major, b [64,128] bf16 row-major (d = a.b). */
 int tdb200_selftest_umma_bf16(const void* a, const void* b, float* d_out, void* stream);
+/* Diagnostics: phase trace of the fused attention kernel.  trace (device, 2*64*8 int64) or NULL to disable; see
+ * sla_attn.cu (g_attn_trace) for the layout.  Synchronises the device (cudaMemcpyToSymbol). */
+int tdb200_debug_set_attn_trace(long long* trace_or_null);
 /* Diagnostics: TMEM->register read throughput.  One CTA per SM, `warps` (4/8/12/16) warps each issuing `iters`
  * tcgen05.ld.32x32b.x64 (8 KB per warp instruction), optionally followed by the GEMM's int->float + FMA dequant.
  * cycles_per_cta [#SMs] receives clock64() deltas. */

@@ -28,3 +28,21 @@ for topk in (4, 13, 26, 51, 102, 204):
     us = ts[len(ts) // 2] * 1e3
     print(json.dumps({"topk_blocks": topk, "us": round(us, 1), "us_per_cta_slot": round(us / (ctas / 296), 2),
                       "ns_per_iter_per_cta": round(us * 1e3 / (ctas / 296) / topk, 1)}))
+
+# ---- phase trace of one softmax warp (see g_attn_trace in sla_attn.cu)
+from turbodiffusion_b200._lib import lib, check, ptr
+trace = torch.zeros(2 * 64 * 8, dtype=torch.int64, device=dev)
+check(lib().tdb200_debug_set_attn_trace(ptr(trace)), "set trace")
+_, lut = block_map_from_pools(prep.q_pool, prep.k_pool, 51)
+attn_fwd(prep, v, q, lut, 51, kvw, ksum, pb, D ** -0.5)
+torch.cuda.synchronize()
+check(lib().tdb200_debug_set_attn_trace(None), "clear trace")
+t = trace.cpu().view(2, 64, 8)
+names = ["wait_S", "ldtm", "max+vote", "exps", "wait_Pfree", "store+publish", "->next"]
+for slot in range(2):
+    tt = t[slot, :51]
+    d = torch.stack([tt[:, k + 1] - tt[:, k] for k in range(6)] + [torch.cat([tt[1:, 0] - tt[:-1, 6], torch.zeros(1, dtype=torch.int64)])], 1).float()
+    per_iter = (tt[1:, 0] - tt[:-1, 0]).float()
+    print(json.dumps({"slot": slot, "iter_cycles_median": per_iter.median().item(), "iter_cycles_mean": per_iter.mean().item(),
+                      "phase_median": {n: d[5:45, i].median().item() for i, n in enumerate(names)},
+                      "loop_total": int(t[slot, 63, 7] - tt[0, 0])}))

@@ -58,7 +58,7 @@ template <typename T, bool kCluster>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // 1024-aligned, stays a shared-space pointer
   uint8_t* c_stage = smem + size_t(kStages) * kStageBytes;  // [kEpiWarps][32 rows][128 B]
   uint64_t* bars = reinterpret_cast<uint64_t*>(c_stage + kEpiWarps * kCStageBytes);
   uint64_t* full_bar = bars;                      // [kStages]  TMA -> MMA

@@ -11,7 +11,7 @@ __global__ void __launch_bounds__(128, 1)
 selftest_umma_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                           float* __restrict__ d_out) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // 1024-aligned, stays a shared-space pointer
   uint8_t* sA = smem;               // 128 rows x 128 B = 16 KB
   uint8_t* sB = smem + 16384;       // 2 chunks x (64 rows x 128 B) = 16 KB
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 32768);

@@ -45,6 +45,15 @@ constexpr uint32_t kColS = 0, kColO = 128;
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kRescaleThreshold = 8.0f;         // log2 domain
 
+// Optional phase trace (diagnostics): when set through tdb200_debug_set_attn_trace(), lane 0 of softmax warp 0 of CTAs
+// (x == 1, y == 0, z == 0) and (x == 3, ...) records clock64() at the phase boundaries of its first 64 iterations:
+// trace[slot][j][0..6] = loop top, S ready, S in registers, max/vote done, exps done, P buffer free, P published.
+__device__ long long* g_attn_trace = nullptr;
+#define TDB_TRACE(slot_ok, j, k)                                                       \
+  do {                                                                                 \
+    if ((slot_ok) && (j) < 64) trace_base[(j) * 8 + (k)] = clock64();                  \
+  } while (0)
+
 struct AttnParams {
   const float* q_scale;   // [b,h,mblk]
   const float* k_scale;   // [b,h,nblk]
@@ -69,7 +78,7 @@ sla_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q8, const __grid_co
                     const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_kvw,
                     AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // 1024-aligned, stays a shared-space pointer
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBars);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kNumBars);
   uint16_t* s_lut = reinterpret_cast<uint16_t*>(smem + kOffLut);                 // [topk] key-block ids
@@ -219,19 +228,26 @@ sla_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q8, const __grid_co
     constexpr int kMagicI = 0x4B400000;
     uint8_t* const sP = smem + kOffP;
 
+    long long* trace_base = nullptr;
+    const bool tracing = g_attn_trace != nullptr && warp == 0 && lane == 0 && hh == 0 && b == 0 && (m_blk == 1 || m_blk == 3);
+    if (tracing) trace_base = g_attn_trace + (m_blk == 1 ? 0 : 64 * 8);
     float m_used = -INFINITY, l_sum = 0.f;
+    // The S tile of block j+1 is pulled out of TMEM while P(j) is being published (Q.K^T runs one block ahead), so the
+    // tcgen05.ld latency no longer sits in front of the row max.
+    uint32_t s0[32], s1[32];
+    mbar_wait(&bars[kBarSFull + 0], 0);
+    tc_fence_after_sync();
+    tmem_ld_x32(tmem_base + lane_addr + kColS, s0);
+    tmem_ld_x32(tmem_base + lane_addr + kColS + 32, s1);
     for (int j = 0; j < T_blocks; ++j) {
+      TDB_TRACE(tracing, j, 0);
       const int st = j & 1;
       const int blk = s_lut[j];
       const float sc = qsc * s_ksc[j];
       const int valid = p.lk - blk * BLKK;              // < 64 only in the ragged last key block
-      mbar_wait(&bars[kBarSFull + st], (j >> 1) & 1);
-      tc_fence_after_sync();
-      uint32_t s0[32], s1[32];
-      const uint32_t ts = tmem_base + lane_addr + kColS + st * BLKK;
-      tmem_ld_x32(ts, s0);
-      tmem_ld_x32(ts + 32, s1);
+      TDB_TRACE(tracing, j, 1);
       tmem_ld_wait();
+      TDB_TRACE(tracing, j, 2);
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars[kBarSEmpty + st]);
@@ -283,6 +299,7 @@ sla_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q8, const __grid_co
         m_used = m_new;
       }
 
+      TDB_TRACE(tracing, j, 3);
       // ---- P = exp2(s*sc - m_used); int->float via the magic-number add keeps the XU pipe free for ex2; the scale+bias
       //      FMA and the row-sum adds run as packed f32x2 instructions.  Masked columns hold INT_MIN (a very negative
       //      score); their exact removal happens in the ragged-block fix-up below.
@@ -327,9 +344,18 @@ sla_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q8, const __grid_co
         }
       }
       l_sum += psum;
+      TDB_TRACE(tracing, j, 4);
+      if (j + 1 < T_blocks) {  // prefetch S(j+1): s0/s1 are dead (P lives in pw)
+        mbar_wait(&bars[kBarSFull + (st ^ 1)], ((j + 1) >> 1) & 1);
+        tc_fence_after_sync();
+        const uint32_t tn = tmem_base + lane_addr + kColS + (st ^ 1) * BLKK;
+        tmem_ld_x32(tn, s0);
+        tmem_ld_x32(tn + 32, s1);
+      }
 
       // ---- P row -> shared memory, K-major SW128: 16-byte chunk c of row r lives at r*128 + ((c ^ (r & 7)) << 4)
       mbar_wait(&bars[kBarPEmpty], (j & 1) ^ 1);     // P.V of block j-1 has finished reading the (single) P buffer
+      TDB_TRACE(tracing, j, 5);
       uint8_t* prow = sP + r * 128;
 #pragma unroll
       for (int c = 0; c < 8; ++c)
@@ -338,7 +364,9 @@ sla_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q8, const __grid_co
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars[kBarPFull]);
+      TDB_TRACE(tracing, j, 6);
     }
+    if (tracing) trace_base[63 * 8 + 7] = clock64();  // loop exit
 
     // ---- linear branch operand: phi(q) = softmax over D of this thread's query row (SLA/core.py:243), rounded to T
     float den = 1e-5f;
@@ -452,6 +480,10 @@ sla_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q8, const __grid_co
 }
 
 }  // namespace
+
+extern "C" int tdb200_debug_set_attn_trace(long long* trace_or_null) {
+  return tdb::check_cuda(cudaMemcpyToSymbol(g_attn_trace, &trace_or_null, sizeof(trace_or_null)), "cudaMemcpyToSymbol(g_attn_trace)");
+}
 
 extern "C" int tdb200_sla_attn_fwd(const int8_t* q_i8, const float* q_scale, const int8_t* k_i8, const float* k_scale,
                                    const void* v, const void* q, int dtype, const int32_t* lut, int64_t topk,

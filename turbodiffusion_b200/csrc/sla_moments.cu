@@ -45,11 +45,11 @@ template <typename T>
 __global__ void __launch_bounds__(kThreads, 1)
 sla_moments_kernel(const __grid_constant__ CUtensorMap tmap_v, MomParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // 1024-aligned, stays a shared-space pointer
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBars);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kNumBars);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int split = blockIdx.x, hh = blockIdx.y, b = blockIdx.z;
+  const int hh = blockIdx.x, split = blockIdx.y, b = blockIdx.z;  // heads fastest (DRAM page locality of [L, H, D])
   const int bh = b * p.h + hh;
   const int my_tiles = (p.tiles - split + p.splits - 1) / p.splits;  // tiles split, split+splits, ...
 
@@ -223,7 +223,7 @@ extern "C" int tdb200_sla_linear_moments(const void* k, const void* v, int dtype
   if (splits < 1) splits = 1;
   if (splits > p.tiles) splits = p.tiles;
   p.splits = splits;
-  dim3 grid(splits, static_cast<unsigned>(h), static_cast<unsigned>(b));
+  dim3 grid(static_cast<unsigned>(h), splits, static_cast<unsigned>(b));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
 #define TDB_MOM(T)                                                                                                  \
   do {                                                                                                              \

@@ -25,7 +25,7 @@ __global__ void __launch_bounds__(256) kmean_partial_kernel(const T* __restrict_
   constexpr int CPR = D / 8;          // 16-byte chunks per row
   constexpr int RPP = 256 / CPR;      // rows per pass
   __shared__ float red[RPP][D];
-  const int chunk = blockIdx.x, hh = blockIdx.y, b = blockIdx.z;
+  const int hh = blockIdx.x, chunk = blockIdx.y, b = blockIdx.z;  // heads fastest: concurrent CTAs read whole [row, H*D] lines
   const int c = threadIdx.x % CPR, r = threadIdx.x / CPR;
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   const int64_t row_begin = int64_t(chunk) * kMeanRows;
@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(ROWS* D / 64) pool_quant_kernel(const T* __res
   static_assert(ROWS / RPP == 8, "8 passes per thread");
   __shared__ float red[RPP][D];
   __shared__ float warp_amax[THREADS / 32];
-  const int blk = blockIdx.x, hh = blockIdx.y, b = blockIdx.z;
+  const int hh = blockIdx.x, blk = blockIdx.y, b = blockIdx.z;  // heads fastest: concurrent CTAs read whole [row, H*D] lines
   const int c = threadIdx.x % CPR, r = threadIdx.x / CPR;
   const int64_t bh = int64_t(b) * h + hh;
 
@@ -153,16 +153,16 @@ int run(const void* q, const void* k, int64_t b, int64_t lq, int64_t l, int64_t 
   const int mblk = static_cast<int>(cdiv64(lq, 128)), nblk = static_cast<int>(cdiv64(l, 64));
   const int chunks = static_cast<int>(cdiv64(l, kMeanRows));
   float* partial = reinterpret_cast<float*>(k_i8);  // scratch: chunks*D*4 bytes per head <= l*D bytes (l*D/64 floats)
-  dim3 g1(chunks, static_cast<unsigned>(h), static_cast<unsigned>(b));
+  dim3 g1(static_cast<unsigned>(h), chunks, static_cast<unsigned>(b));
   kmean_partial_kernel<T, D><<<g1, 256, 0, st>>>(static_cast<const T*>(k), partial, l, static_cast<int>(h), chunks);
   if (int rc = check_launch("kmean_partial_kernel")) return rc;
   kmean_final_kernel<<<static_cast<unsigned>(b * h), 128, 0, st>>>(partial, kmean, l, chunks, D);
   if (int rc = check_launch("kmean_final_kernel")) return rc;
-  dim3 gq(mblk, static_cast<unsigned>(h), static_cast<unsigned>(b));
+  dim3 gq(static_cast<unsigned>(h), mblk, static_cast<unsigned>(b));
   pool_quant_kernel<T, D, 128, false><<<gq, 128 * D / 64, 0, st>>>(static_cast<const T*>(q), nullptr, q_i8, q_scale,
                                                                    static_cast<T*>(q_pool), lq, static_cast<int>(h), mblk);
   if (int rc = check_launch("pool_quant_kernel<q>")) return rc;
-  dim3 gk(nblk, static_cast<unsigned>(h), static_cast<unsigned>(b));
+  dim3 gk(static_cast<unsigned>(h), nblk, static_cast<unsigned>(b));
   pool_quant_kernel<T, D, 64, true><<<gk, 64 * D / 64, 0, st>>>(static_cast<const T*>(k), kmean, k_i8, k_scale,
                                                                 static_cast<T*>(k_pool), l, static_cast<int>(h), nblk);
   return check_launch("pool_quant_kernel<k>");
@@ -178,7 +178,8 @@ extern "C" int tdb200_sla_quant_qk(const void* q, const void* k, int dtype, int6
     return fail(TDB200_ERR_INVALID_ARG, "sla_quant_qk: null pointer");
   if (b <= 0 || l <= 0 || lq <= 0 || h <= 0) return fail(TDB200_ERR_INVALID_ARG, "sla_quant_qk: bad shape");
   if (d != 64 && d != 128) return fail(TDB200_ERR_UNSUPPORTED, "sla_quant_qk: head dim %lld (64 or 128, SLA/core.py:207)", (long long)d);
-  if (h > 65535 || b > 65535) return fail(TDB200_ERR_UNSUPPORTED, "sla_quant_qk: h or b too large");
+  if (h > 65535 || b > 65535 || cdiv64(l, 64) > 65535 || cdiv64(lq, 128) > 65535)
+    return fail(TDB200_ERR_UNSUPPORTED, "sla_quant_qk: h, b or sequence length too large");
   if (!aligned16(q) || !aligned16(k) || !aligned16(q_i8) || !aligned16(k_i8))
     return fail(TDB200_ERR_INVALID_ARG, "sla_quant_qk: buffers must be 16-byte aligned");
   if (int rc = require_sm100()) return rc;
