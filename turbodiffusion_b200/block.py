@@ -28,24 +28,25 @@ LINEARS = ("self_attn.q", "self_attn.k", "self_attn.v", "self_attn.o", "cross_at
 def random_block_state(dim: int, ffn_dim: int, heads: int, seed: int, device, dtype=torch.bfloat16) -> Dict[str, torch.Tensor]:
     """Random-init weights of one block in the reference's quantised state-dict layout (modify_model.py:156-183:
     Int8Linear.from_linear quantises nn.Linear weights with int8_quant)."""
-    g = torch.Generator(device="cpu").manual_seed(seed)
+    gdev = torch.device(device)
+    g = torch.Generator(device=gdev).manual_seed(seed)  # generated on the target device (14B-parameter shapes)
     sd: Dict[str, torch.Tensor] = {}
     shapes = {"self_attn.q": (dim, dim), "self_attn.k": (dim, dim), "self_attn.v": (dim, dim), "self_attn.o": (dim, dim),
               "cross_attn.q": (dim, dim), "cross_attn.k": (dim, dim), "cross_attn.v": (dim, dim),
               "cross_attn.o": (dim, dim), "ffn.0": (ffn_dim, dim), "ffn.2": (dim, ffn_dim)}
     for name, (n, k) in shapes.items():
-        w = (torch.randn(n, k, generator=g) * (k ** -0.5)).to(dtype).to(device)
+        w = (torch.randn(n, k, generator=g, device=gdev) * (k ** -0.5)).to(dtype)
         q, s = ops.int8_quant(w)
         sd[name + ".int8_weight"], sd[name + ".scale"] = q, s
-        sd[name + ".bias"] = (torch.randn(n, generator=g) * 0.02).to(dtype).to(device)
+        sd[name + ".bias"] = (torch.randn(n, generator=g, device=gdev) * 0.02).to(dtype)
     for name in ("self_attn.norm_q", "self_attn.norm_k", "cross_attn.norm_q", "cross_attn.norm_k"):
-        sd[name + ".weight"] = (1.0 + 0.1 * torch.randn(dim, generator=g)).float().to(device)
-    sd["norm3.weight"] = (1.0 + 0.1 * torch.randn(dim, generator=g)).float().to(device)
-    sd["norm3.bias"] = (0.05 * torch.randn(dim, generator=g)).float().to(device)
-    sd["modulation"] = (torch.randn(1, 6, dim, generator=g) / dim ** 0.5).float().to(device)
+        sd[name + ".weight"] = (1.0 + 0.1 * torch.randn(dim, generator=g, device=gdev)).float()
+    sd["norm3.weight"] = (1.0 + 0.1 * torch.randn(dim, generator=g, device=gdev)).float()
+    sd["norm3.bias"] = (0.05 * torch.randn(dim, generator=g, device=gdev)).float()
+    sd["modulation"] = (torch.randn(1, 6, dim, generator=g, device=gdev) / dim ** 0.5).float()
     d = dim // heads
-    sd["self_attn.attn_op.local_attn.proj_l.weight"] = (torch.randn(d, d, generator=g) * 0.05).float().to(device)
-    sd["self_attn.attn_op.local_attn.proj_l.bias"] = (torch.randn(d, generator=g) * 0.05).float().to(device)
+    sd["self_attn.attn_op.local_attn.proj_l.weight"] = (torch.randn(d, d, generator=g, device=gdev) * 0.05).float()
+    sd["self_attn.attn_op.local_attn.proj_l.bias"] = (torch.randn(d, generator=g, device=gdev) * 0.05).float()
     return sd
 
 
