@@ -144,6 +144,8 @@ int tdb200_rms_norm_rope(const void* x, int dtype, const float* w, const float* 
  *     q_i8   [b,h,l,d] int8, q_scale [b,h,mblk];  k_i8 [b,h,l,d] int8 of T(k - T(kmean)), k_scale [b,h,nblk]
  *                             scale = amax/127 + 1e-7, round half away from zero (SpargeAttn get_vanilla_qk_quant)
  *     q_pool [b,h,mblk,d] T,  k_pool [b,h,nblk,d] T   block means (SLA/utils.py:21-52; actual row count in the tail)
+ *     q == NULL or k == NULL runs only the other half (the sequence-parallel path prepares Q while the K/V all-gather
+ *     is still in flight).
  * tdb200_sla_block_map  pooled score T(q_pool . k_pool^T), top-`topk` per row (ties -> lowest index),
  *     sparse_map [b,h,mblk,nblk] int8 0/1 (SLA/utils.py:64-66) and lut [b,h,mblk,topk] int32 ascending block ids.
  * tdb200_sla_linear_moments   phi = softmax over d;  kv [b,h,d(v),d(k)] fp32 = sum_l v[l,:]^T phi(k)[l,:],

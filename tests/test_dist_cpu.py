@@ -42,7 +42,7 @@ class OraclePrims:
         vh = v.transpose(1, 2).float()
         return vh.transpose(-1, -2) @ phi, phi.sum(-2)                            # kv [1,H,dv,dk], ksum [1,H,D]
 
-    def attention(self, q, k_full, v_full, lk, kv, ksum):
+    def attention(self, q, k_full, v_full, lk, kv, ksum, qprep=None):
         O = self.O
         qh = q.transpose(1, 2).contiguous()
         kh = k_full[:, :lk].transpose(1, 2).contiguous()

@@ -47,6 +47,36 @@ def quant_qk(q: torch.Tensor, k: torch.Tensor, lk: int = None) -> QKPrep:
     return o
 
 
+def quant_q_only(q: torch.Tensor) -> QKPrep:
+    """The query half of quant_qk (pooled means + Sage INT8 of q); fill in the key half later with quant_k_into()."""
+    require_cuda(q)
+    b, lq, h, d = q.shape
+    dev = q.device
+    o = QKPrep()
+    o.mblk = cdiv(lq, 128)
+    o.q_i8 = torch.empty(b, h, lq, d, dtype=torch.int8, device=dev)
+    o.q_scale = torch.empty(b, h, o.mblk, dtype=torch.float32, device=dev)
+    o.q_pool = torch.empty(b, h, o.mblk, d, dtype=q.dtype, device=dev)
+    check(lib().tdb200_sla_quant_qk(ptr(q), None, DTYPE_TAG[q.dtype], b, lq, lq, h, d, None, ptr(o.q_i8), ptr(o.q_scale), None,
+                                    None, ptr(o.q_pool), None, stream_ptr(dev)), "sla_quant_qk")
+    return o
+
+
+def quant_k_into(o: QKPrep, k: torch.Tensor, lk: int) -> QKPrep:
+    """The key half of quant_qk on the first `lk` rows of k [B, >=lk, H, D]."""
+    require_cuda(k)
+    b, _, h, d = k.shape
+    dev = k.device
+    o.nblk = cdiv(lk, 64)
+    o.kmean = torch.empty(b, h, d, dtype=torch.float32, device=dev)
+    o.k_i8 = torch.empty(b, h, lk, d, dtype=torch.int8, device=dev)
+    o.k_scale = torch.empty(b, h, o.nblk, dtype=torch.float32, device=dev)
+    o.k_pool = torch.empty(b, h, o.nblk, d, dtype=k.dtype, device=dev)
+    check(lib().tdb200_sla_quant_qk(None, ptr(k), DTYPE_TAG[k.dtype], b, lk, lk, h, d, ptr(o.kmean), None, None, ptr(o.k_i8),
+                                    ptr(o.k_scale), None, ptr(o.k_pool), stream_ptr(dev)), "sla_quant_qk")
+    return o
+
+
 def block_map_from_pools(q_pool: torch.Tensor, k_pool: torch.Tensor, topk: int):
     """Pooled score + top-k (SLA/utils.py:59-66).  Returns (sparse_map int8 [B,H,Mblk,Nblk], lut int32 ascending)."""
     b, h, mblk, d = q_pool.shape

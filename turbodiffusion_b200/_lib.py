@@ -82,7 +82,7 @@ def lib() -> ctypes.CDLL:
 
 
 LAUNCHES = 0  # kernels launched through the C ABI (each entry point documents how many it enqueues)
-_KERNELS_PER_CALL = {"sla_quant_qk": 4, "layernorm_modulate_quant": 2}
+_KERNELS_PER_CALL = {"sla_quant_qk": 4, "layernorm_modulate_quant": 2}  # upper bounds per entry point
 
 
 def check(rc: int, what: str) -> None:

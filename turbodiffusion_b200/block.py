@@ -90,12 +90,15 @@ class WanBlockB200:
             xq, xs = ops.layernorm_modulate_quant(x, e[1], e[0], eps)
         else:
             xq, xs = ops.layernorm_modulate_quant_from_stats(x, stats, e[1], e[0])
-        q = self._gemm(xq, xs, "self_attn.q", x.dtype)
+        # K and V first: a sequence-parallel attention hook starts their all-gather while Q is still being produced
         k = self._gemm(xq, xs, "self_attn.k", x.dtype)
         v = self._gemm(xq, xs, "self_attn.v", x.dtype)
-        q = ops.rmsnorm_rope(q, sd["self_attn.norm_q.weight"], angles, eps, h)
         k = ops.rmsnorm_rope(k, sd["self_attn.norm_k.weight"], angles, eps, h)
         attn = self.attn_hook or self.sla
+        if hasattr(attn, "start_kv"):
+            attn.start_kv(k.view(1, l, h, d), v.view(1, l, h, d))
+        q = self._gemm(xq, xs, "self_attn.q", x.dtype)
+        q = ops.rmsnorm_rope(q, sd["self_attn.norm_q.weight"], angles, eps, h)
         a = attn(q.view(1, l, h, d), k.view(1, l, h, d), v.view(1, l, h, d)).reshape(l, dim)
         y = self._linear(a, "self_attn.o")
         x = ops.gate_residual(x, y, e[2])  # x + y * e[2] (:405-406)

@@ -148,9 +148,18 @@ __global__ void __launch_bounds__(ROWS* D / 64) pool_quant_kernel(const T* __res
 }
 
 template <typename T, int D>
-int run(const void* q, const void* k, int64_t b, int64_t lq, int64_t l, int64_t h, float* kmean, int8_t* q_i8,
-        float* q_scale, int8_t* k_i8, float* k_scale, void* q_pool, void* k_pool, cudaStream_t st) {
-  const int mblk = static_cast<int>(cdiv64(lq, 128)), nblk = static_cast<int>(cdiv64(l, 64));
+int run_q(const void* q, int64_t b, int64_t lq, int64_t h, int8_t* q_i8, float* q_scale, void* q_pool, cudaStream_t st) {
+  const int mblk = static_cast<int>(cdiv64(lq, 128));
+  dim3 gq(static_cast<unsigned>(h), mblk, static_cast<unsigned>(b));
+  pool_quant_kernel<T, D, 128, false><<<gq, 128 * D / 64, 0, st>>>(static_cast<const T*>(q), nullptr, q_i8, q_scale,
+                                                                   static_cast<T*>(q_pool), lq, static_cast<int>(h), mblk);
+  return check_launch("pool_quant_kernel<q>");
+}
+
+template <typename T, int D>
+int run_k(const void* k, int64_t b, int64_t l, int64_t h, float* kmean, int8_t* k_i8, float* k_scale, void* k_pool,
+          cudaStream_t st) {
+  const int nblk = static_cast<int>(cdiv64(l, 64));
   const int chunks = static_cast<int>(cdiv64(l, kMeanRows));
   float* partial = reinterpret_cast<float*>(k_i8);  // scratch: chunks*D*4 bytes per head <= l*D bytes (l*D/64 floats)
   dim3 g1(static_cast<unsigned>(h), chunks, static_cast<unsigned>(b));
@@ -158,14 +167,20 @@ int run(const void* q, const void* k, int64_t b, int64_t lq, int64_t l, int64_t 
   if (int rc = check_launch("kmean_partial_kernel")) return rc;
   kmean_final_kernel<<<static_cast<unsigned>(b * h), 128, 0, st>>>(partial, kmean, l, chunks, D);
   if (int rc = check_launch("kmean_final_kernel")) return rc;
-  dim3 gq(static_cast<unsigned>(h), mblk, static_cast<unsigned>(b));
-  pool_quant_kernel<T, D, 128, false><<<gq, 128 * D / 64, 0, st>>>(static_cast<const T*>(q), nullptr, q_i8, q_scale,
-                                                                   static_cast<T*>(q_pool), lq, static_cast<int>(h), mblk);
-  if (int rc = check_launch("pool_quant_kernel<q>")) return rc;
   dim3 gk(static_cast<unsigned>(h), nblk, static_cast<unsigned>(b));
   pool_quant_kernel<T, D, 64, true><<<gk, 64 * D / 64, 0, st>>>(static_cast<const T*>(k), kmean, k_i8, k_scale,
                                                                 static_cast<T*>(k_pool), l, static_cast<int>(h), nblk);
   return check_launch("pool_quant_kernel<k>");
+}
+
+template <typename T, int D>
+int run(const void* q, const void* k, int64_t b, int64_t lq, int64_t l, int64_t h, float* kmean, int8_t* q_i8,
+        float* q_scale, int8_t* k_i8, float* k_scale, void* q_pool, void* k_pool, cudaStream_t st) {
+  if (q != nullptr)
+    if (int rc = run_q<T, D>(q, b, lq, h, q_i8, q_scale, q_pool, st)) return rc;
+  if (k != nullptr)
+    if (int rc = run_k<T, D>(k, b, l, h, kmean, k_i8, k_scale, k_pool, st)) return rc;
+  return TDB200_OK;
 }
 
 }  // namespace
@@ -174,13 +189,13 @@ extern "C" int tdb200_sla_quant_qk(const void* q, const void* k, int dtype, int6
                                    int64_t d, float* kmean, int8_t* q_i8, float* q_scale, int8_t* k_i8, float* k_scale,
                                    void* q_pool, void* k_pool, void* stream) {
   using namespace tdb;
-  if (!q || !k || !kmean || !q_i8 || !q_scale || !k_i8 || !k_scale || !q_pool || !k_pool)
+  if ((!q && !k) || (q && (!q_i8 || !q_scale || !q_pool)) || (k && (!kmean || !k_i8 || !k_scale || !k_pool)))
     return fail(TDB200_ERR_INVALID_ARG, "sla_quant_qk: null pointer");
   if (b <= 0 || l <= 0 || lq <= 0 || h <= 0) return fail(TDB200_ERR_INVALID_ARG, "sla_quant_qk: bad shape");
   if (d != 64 && d != 128) return fail(TDB200_ERR_UNSUPPORTED, "sla_quant_qk: head dim %lld (64 or 128, SLA/core.py:207)", (long long)d);
   if (h > 65535 || b > 65535 || cdiv64(l, 64) > 65535 || cdiv64(lq, 128) > 65535)
     return fail(TDB200_ERR_UNSUPPORTED, "sla_quant_qk: h, b or sequence length too large");
-  if (!aligned16(q) || !aligned16(k) || !aligned16(q_i8) || !aligned16(k_i8))
+  if ((q && (!aligned16(q) || !aligned16(q_i8))) || (k && (!aligned16(k) || !aligned16(k_i8))))
     return fail(TDB200_ERR_INVALID_ARG, "sla_quant_qk: buffers must be 16-byte aligned");
   if (int rc = require_sm100()) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);

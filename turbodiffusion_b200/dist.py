@@ -44,12 +44,16 @@ class GpuPrimitives:
     def __init__(self, sla_module):
         self.sla = sla_module
 
-    def attention(self, q, k_full, v_full, lk, kv, ksum):
+    def prepare_q(self, q):
+        from .SLA.utils import quant_q_only
+        return quant_q_only(q)
+
+    def attention(self, q, k_full, v_full, lk, kv, ksum, qprep=None):
         from .SLA.core import attn_fwd
-        from .SLA.utils import block_map_from_pools, quant_qk
+        from .SLA.utils import block_map_from_pools, quant_k_into, quant_q_only
         sla = self.sla
         d = q.shape[-1]
-        prep = quant_qk(q, k_full, lk)
+        prep = quant_k_into(qprep if qprep is not None else quant_q_only(q), k_full, lk)
         topk = min(prep.nblk, int(sla.topk * prep.nblk))
         _, lut = block_map_from_pools(prep.q_pool, prep.k_pool, topk)
         kvw = torch.matmul(sla.proj_l.weight.float(), kv).to(q.dtype).contiguous()
@@ -61,14 +65,19 @@ class GpuPrimitives:
 
 
 class SPAttention:
-    """Drop-in for the block's attention callable: (q, k, v) local [1, rows, H, D] -> [1, rows, H, D]."""
+    """Drop-in for the block's attention callable: (q, k, v) local [1, rows, H, D] -> [1, rows, H, D].
+
+    The block calls start_kv(k, v) as soon as K and V exist: both all-gathers and the moment all-reduces are issued
+    asynchronously (NCCL stream) and overlap with the Q projection, Q RMSNorm+RoPE and the Q-side quantisation that the
+    block and __call__ run before waiting on them."""
 
     def __init__(self, sp: "SequenceParallel", prims):
         self.sp, self.prims = sp, prims
         self._bufs = {}
+        self._pending = None
 
-    def _gather(self, name: str, t: torch.Tensor) -> torch.Tensor:
-        """t [1, rows, H, D] -> [1, world*rows_pad, H, D] (zero padded tail of the last rank)."""
+    def _gather_async(self, name: str, t: torch.Tensor):
+        """t [1, rows, H, D] -> ([1, world*rows_pad, H, D] buffer, NCCL work handle); zero-padded tail of the last rank."""
         sp = self.sp
         _, rows, h, d = t.shape
         key = (name, h, d, t.dtype, t.device)
@@ -77,20 +86,34 @@ class SPAttention:
                                torch.zeros(sp.world * sp.rows_pad, h, d, dtype=t.dtype, device=t.device))
         send, recv = self._bufs[key]
         send[:rows].copy_(t[0])
-        dist.all_gather_into_tensor(recv, send, group=sp.group)
-        return recv.unsqueeze(0)
+        work = dist.all_gather_into_tensor(recv, send, group=sp.group, async_op=True)
+        return recv.unsqueeze(0), work
+
+    def _cdt(self, t):
+        return self.prims.sla.dtype if hasattr(self.prims, "sla") else t.dtype
+
+    def start_kv(self, k, v):
+        sp = self.sp
+        cdt = self._cdt(k)
+        k, v = k.to(cdt).contiguous(), v.to(cdt).contiguous()
+        k_full, wk = self._gather_async("k", k)
+        v_full, wv = self._gather_async("v", v)
+        kv, ksum = self.prims.moments(k, v)
+        w1 = dist.all_reduce(kv, group=sp.group, async_op=True)
+        w2 = dist.all_reduce(ksum, group=sp.group, async_op=True)
+        self._pending = (k_full, v_full, kv, ksum, (wk, wv, w1, w2))
 
     def __call__(self, q, k, v):
-        sp = self.sp
         dtype = q.dtype
-        cdt = self.prims.sla.dtype if hasattr(self.prims, "sla") else dtype
-        q, k, v = (t.to(cdt).contiguous() for t in (q, k, v))
-        k_full = self._gather("k", k)
-        v_full = self._gather("v", v)
-        kv, ksum = self.prims.moments(k, v)
-        dist.all_reduce(kv, group=sp.group)
-        dist.all_reduce(ksum, group=sp.group)
-        out = self.prims.attention(q, k_full, v_full, sp.total_rows, kv, ksum)
+        q = q.to(self._cdt(q)).contiguous()
+        if self._pending is None:
+            self.start_kv(k, v)
+        k_full, v_full, kv, ksum, works = self._pending
+        self._pending = None
+        qprep = self.prims.prepare_q(q) if hasattr(self.prims, "prepare_q") else None  # overlaps with the collectives
+        for w in works:
+            w.wait()
+        out = self.prims.attention(q, k_full, v_full, self.sp.total_rows, kv, ksum, qprep)
         return out.to(dtype)
 
 
