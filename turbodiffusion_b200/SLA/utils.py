@@ -58,7 +58,7 @@ def quant_q_only(q: torch.Tensor) -> QKPrep:
     o.q_scale = torch.empty(b, h, o.mblk, dtype=torch.float32, device=dev)
     o.q_pool = torch.empty(b, h, o.mblk, d, dtype=q.dtype, device=dev)
     check(lib().tdb200_sla_quant_qk(ptr(q), None, DTYPE_TAG[q.dtype], b, lq, lq, h, d, None, ptr(o.q_i8), ptr(o.q_scale), None,
-                                    None, ptr(o.q_pool), None, stream_ptr(dev)), "sla_quant_qk")
+                                    None, ptr(o.q_pool), None, stream_ptr(dev)), "sla_quant_qk", launches=1)
     return o
 
 
@@ -73,7 +73,7 @@ def quant_k_into(o: QKPrep, k: torch.Tensor, lk: int) -> QKPrep:
     o.k_scale = torch.empty(b, h, o.nblk, dtype=torch.float32, device=dev)
     o.k_pool = torch.empty(b, h, o.nblk, d, dtype=k.dtype, device=dev)
     check(lib().tdb200_sla_quant_qk(None, ptr(k), DTYPE_TAG[k.dtype], b, lk, lk, h, d, ptr(o.kmean), None, None, ptr(o.k_i8),
-                                    ptr(o.k_scale), None, ptr(o.k_pool), stream_ptr(dev)), "sla_quant_qk")
+                                    ptr(o.k_scale), None, ptr(o.k_pool), stream_ptr(dev)), "sla_quant_qk", launches=3)
     return o
 
 

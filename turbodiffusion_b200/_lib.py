@@ -85,9 +85,9 @@ LAUNCHES = 0  # kernels launched through the C ABI (each entry point documents h
 _KERNELS_PER_CALL = {"sla_quant_qk": 4, "layernorm_modulate_quant": 2}  # upper bounds per entry point
 
 
-def check(rc: int, what: str) -> None:
+def check(rc: int, what: str, launches: int = None) -> None:
     global LAUNCHES
-    LAUNCHES += _KERNELS_PER_CALL.get(what, 1)
+    LAUNCHES += _KERNELS_PER_CALL.get(what, 1) if launches is None else launches
     if rc != 0:
         msg = lib().tdb200_last_error()
         raise Tdb200Error(f"{what} failed (code {rc}): {msg.decode() if msg else ''}")

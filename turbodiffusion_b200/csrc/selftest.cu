@@ -109,8 +109,11 @@ __global__ void __launch_bounds__(512, 1) tmem_read_probe_kernel(int iters, long
     if (kConvert) {
 #pragma unroll
       for (int j = 0; j < 64; ++j) acc[j] = fmaf(__int2float_rn(static_cast<int>(r[j])), 1.0001f, acc[j]);
-    } else {
-      acc[i & 63] += __uint_as_float(r[i & 63]);
+    } else {  // load only: fold the registers with cheap xors so the load cannot be optimised away
+      uint32_t x = 0;
+#pragma unroll
+      for (int j = 0; j < 64; ++j) x ^= r[j];
+      acc[0] += __uint_as_float(x & 0x3f800000u);
     }
   }
   __syncthreads();
