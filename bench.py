@@ -174,6 +174,24 @@ def run_reference(args, shape, rank, world):
 
 
 # ------------------------------------------------------------------------------------------------ B200 arm
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE gemm_w8a8 launch from the committed `ncu --set full` summary
+    (profiles/r01_ncu_gemm_final.txt: the ffn2 GEMM, M=32760 K=8960 N=1536, algorithmic bytes 293.5+13.8+100.6 = 407.9 MB).
+    The roofline above is tensor-bound; traffic ~= algorithmic bytes shows no operand is re-read from HBM."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_ncu_gemm_final.txt")
+    try:
+        tot = 0.0
+        for ln in open(path):
+            for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                if ln.strip().startswith(key + " ="):
+                    val, unit = ln.split("=")[1].split()[:2]
+                    tot += float(val) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[unit]
+        return {"traffic": tot or None, "traffic_algorithmic": 407.9e6,
+                "traffic_source": "profiles/r01_ncu_gemm_final.txt (ffn2 GEMM 32760x8960x1536, one launch)"}
+    except OSError:
+        return {"traffic": None}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -350,7 +368,7 @@ def main():
                          "peak": pk.get("bf16_tflops_sustained"), "unit": "TFLOP/s",
                          "frac": achieved / pk["bf16_tflops_sustained"] if pk.get("bf16_tflops_sustained") else None,
                          "peak_source": f"{pk['_source']} bf16 sustained (no INT8 peak in MEASURED_PEAKS.json; INT8 nominal is 2x bf16)",
-                         "launches": n_gemm, "share_of_step": gemm_share, "traffic": None,
+                         "launches": n_gemm, "share_of_step": gemm_share, **ncu_traffic(),
                          "timed_in": "eager pass of the same K steps (CUDA events around each GEMM launch on the launch stream)"},
             "ms_per_step_eager": ms_eager, "launch_mode": graph_note,
             "clocks": clk.summary(),

@@ -428,6 +428,25 @@ def ltx_rms_norm(x: torch.Tensor, eps: float = 1e-6) -> torch.Tensor:
     return x * torch.rsqrt(x.float().pow(2).mean(-1, keepdim=True) + eps).to(x.dtype)
 
 
+def ltx_row_quant_int8(x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """ltx_distillation/tilelang_w8a8.py:16-36: scale = max(amax,1e-4)/127; round half away; clip [-128,127]."""
+    xf = x.float()
+    scale = xf.abs().amax(-1).clamp_min(1e-4) / 127.0
+    y = xf / scale[:, None]
+    r = torch.where(y >= 0, torch.floor(y + 0.5), torch.ceil(y - 0.5)).clamp_(-128, 127)
+    return r.to(torch.int8), scale
+
+
+def ltx_gemm_post_scale(a_q, a_s, b_q, b_s, bias, out_dtype=torch.bfloat16) -> torch.Tensor:
+    """tilelang_w8a8.py:108-114: C = int32_acc * sA[i] * sB[j] + bias[j] (fp32, left to right), cast to bf16."""
+    acc = (a_q.double() @ b_q.double().t())                       # exact integer accumulation (|sum| < 2^53)
+    f = acc.float()                                               # int32 -> fp32, round to nearest
+    y = (f * a_s[:, None]) * b_s[None, :]
+    if bias is not None:
+        y = y + bias.float()[None, :]
+    return y.to(out_dtype)
+
+
 # =============================================================================================
 # One Wan DiT block's self-attention + FFN hot path (for bench cpu_baseline / block parity), wan2pt1.py:390-417
 # =============================================================================================

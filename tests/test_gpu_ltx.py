@@ -51,3 +51,28 @@ def test_ltx_split_rope(cuda):
     ref = ref.transpose(1, 2).reshape(b, t, h * d)
     got = ltx.apply_split_rotary_emb(x.to(cuda), cos.to(cuda), sin.to(cuda))
     _close(got, ref)
+
+
+@pytest.mark.parametrize("m,n,k", [(256, 512, 256), (300, 384, 1024), (1000, 4096, 4096)])
+def test_ltx_post_scale_w8a8_bit_exact(cuda, m, n, k):
+    """Per-row quant + int32-accumulate GEMM with one post-scale epilogue (tilelang_w8a8.py) against the oracle."""
+    from oracle import td_oracle as O
+    from turbodiffusion_b200 import ltx
+    torch.manual_seed(m + n + k)
+    x = (torch.randn(m, k) * 2).bfloat16()
+    x[:, ::61] *= 12
+    w = (torch.randn(n, k) * 0.05).bfloat16()
+    bias = torch.randn(n).bfloat16()
+    xq_ref, xs_ref = O.ltx_row_quant_int8(x)
+    wq_ref, ws_ref = O.ltx_row_quant_int8(w)
+    xq, xs = ltx.row_quant_int8(x.to(cuda))
+    assert torch.equal(xs.cpu(), xs_ref) and torch.equal(xq.cpu(), xq_ref)
+    y_ref = O.ltx_gemm_post_scale(xq_ref, xs_ref, wq_ref, ws_ref, bias)
+    y = ltx.gemm_int8_post_scale_bias(xq, xs, wq_ref.to(cuda), ws_ref.to(cuda), bias.to(cuda)).cpu()
+    assert torch.equal(y.view(torch.int16), y_ref.view(torch.int16)), (y.float() - y_ref.float()).abs().max()
+    lin = torch.nn.Linear(k, n).to(cuda).bfloat16()
+    mod = ltx.PostScaleInt8Linear.from_linear(lin)
+    out = mod(x.to(cuda).reshape(2, m // 2, k))
+    ref = torch.nn.functional.linear(x.to(cuda).float(), lin.weight.float(), lin.bias.float())
+    # per-row scales with 12x outlier columns in x: a few % of relative error is inherent to this quantisation scheme
+    assert O.stats(out.reshape(m, n).float().cpu(), ref.cpu())["rel_l2"] < 8e-2

@@ -113,6 +113,20 @@ def main():
                 record(full, med, mn, bytes_=nbytes)
         del x
 
+    # LTX-2 per-row post-scale W8A8 (no per-K-block dequant): M = 28672 video tokens, dim 4096, ffn 16384
+    from turbodiffusion_b200 import ltx
+    for name, m, n, k in [("ltx_proj", 28672, 4096, 4096), ("ltx_ffn_up", 28672, 16384, 4096), ("ltx_ffn_down", 28672, 4096, 16384)]:
+        full = f"gemm_w8a8_rowwise/C/{name}/{m}x{n}x{k}"
+        if args.filter not in full:
+            continue
+        a = torch.randint(-128, 128, (m, k), device=dev, dtype=torch.int8)
+        b = torch.randint(-128, 128, (n, k), device=dev, dtype=torch.int8)
+        a_s, b_s = torch.rand(m, device=dev) * 0.01, torch.rand(n, device=dev) * 0.01
+        bias = torch.randn(n, device=dev).bfloat16()
+        med, mn = timeit(lambda: ltx.gemm_int8_post_scale_bias(a, a_s, b, b_s, bias), args.iters)
+        record(full, med, mn, flops=2.0 * m * n * k, bytes_=m * k + n * k + 2 * m * n)
+        del a, b
+
     with open(args.out, "w") as f:
         for r in results:
             f.write(json.dumps(r) + "\n")

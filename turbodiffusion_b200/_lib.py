@@ -45,6 +45,8 @@ _PROTOS = {
     "tdb200_ltx_modulate_ada": [_P, _I, _P, _P, _I, _I, _I, _P, _I64, _I64, _I64, _I64, _P],
     "tdb200_ltx_gated_residual_ada": [_P, _P, _I, _P, _P, _I, _I, _P, _I64, _I64, _I64, _I64, _P],
     "tdb200_ltx_split_rope": [_P, _P, _P, _I, _P, _I64, _I64, _I64, _I64, _P],
+    "tdb200_quant_int8_rowwise": [_P, _I, _I64, _I64, _P, _P, _P],
+    "tdb200_gemm_w8a8_rowwise": [_P, _P, _P, _P, _P, _P, _I, _I64, _I64, _I64, _P],
     "tdb200_debug_set_attn_trace": [_P],
     "tdb200_selftest_umma_bf16": [_P, _P, _P, _P],
     "tdb200_selftest_tmem_read": [_I, _I, _I, _P, _P, _P],

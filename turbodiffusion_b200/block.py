@@ -91,10 +91,12 @@ class WanBlockB200:
         else:
             xq, xs = ops.layernorm_modulate_quant_from_stats(x, stats, e[1], e[0])
         # K and V first: a sequence-parallel attention hook starts their all-gather while Q is still being produced
-        k = self._gemm(xq, xs, "self_attn.k", x.dtype)
-        v = self._gemm(xq, xs, "self_attn.v", x.dtype)
-        k = ops.rmsnorm_rope(k, sd["self_attn.norm_k.weight"], angles, eps, h)
         attn = self.attn_hook or self.sla
+        k = self._gemm(xq, xs, "self_attn.k", x.dtype)
+        k = ops.rmsnorm_rope(k, sd["self_attn.norm_k.weight"], angles, eps, h)
+        if hasattr(attn, "start_k"):
+            attn.start_k(k.view(1, l, h, d))
+        v = self._gemm(xq, xs, "self_attn.v", x.dtype)
         if hasattr(attn, "start_kv"):
             attn.start_kv(k.view(1, l, h, d), v.view(1, l, h, d))
         q = self._gemm(xq, xs, "self_attn.q", x.dtype)

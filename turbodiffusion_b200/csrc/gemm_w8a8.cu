@@ -54,7 +54,10 @@ struct GemmParams {
 // loads its own A tile and HALF of the shared B tile, multicasting that half to both CTAs: 32 KB instead of 48 KB cross
 // the L2->SM fabric per CTA and K-block.  A stage may only be refilled when BOTH CTAs' MMAs have released it, so the
 // stage-empty barriers count 2 arrivals and the MMA warps commit to both CTAs.
-template <typename T, bool kCluster>
+// kRowScale: the LTX-2 client's variant (TurboT2AV ltx_distillation/tilelang_w8a8.py:78-117): a_s [m] per activation row,
+// b_s [n] per output channel, int32 accumulation over ALL of K inside TMEM and ONE epilogue per tile
+// c = T(float(acc) * a_s[i] * b_s[j] + bias[j]).  No per-K-block dequant, so the tensor pipe is the limiter.
+template <typename T, bool kCluster, bool kRowScale>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -127,12 +130,14 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(kDFmtS32, kFmtS8, kFmtS8, 0, 0, BM, BN);
-      uint32_t it = 0;
-      for (int work = work_first; work < p.total_tiles; work += work_stride) {
+      uint32_t it = 0, tile_it = 0;
+      for (int work = work_first; work < p.total_tiles; work += work_stride, ++tile_it) {
         for (int kb = 0; kb < p.k_blocks; ++kb, ++it) {
           const uint32_t stage = it % kStages, phase = (it / kStages) & 1u;
-          const uint32_t buf = it & 1u, bphase = (it >> 1) & 1u;
-          mbar_wait(&tmem_empty[buf], bphase ^ 1u);
+          // per-block mode: one TMEM buffer per K-block; row-scale mode: one buffer per tile
+          const uint32_t bi = kRowScale ? tile_it : it;
+          const uint32_t buf = bi & 1u, bphase = (bi >> 1) & 1u;
+          if (!kRowScale || kb == 0) mbar_wait(&tmem_empty[buf], bphase ^ 1u);
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after_sync();
           const uint32_t sa = smem_u32(smem + size_t(stage) * kStageBytes);
@@ -142,10 +147,11 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
           for (int ks = 0; ks < BK / 32; ++ks) {
             // advance 32 bytes (one K=32 int8 slice) inside the 128B swizzle row: +2 in 16-byte units
-            umma_i8_ss(d, adesc + uint64_t(ks * 2), bdesc + uint64_t(ks * 2), idesc, ks > 0 ? 1u : 0u);
+            umma_i8_ss(d, adesc + uint64_t(ks * 2), bdesc + uint64_t(ks * 2), idesc,
+                       (ks > 0 || (kRowScale && kb > 0)) ? 1u : 0u);
           }
           if (kCluster) umma_commit_mcast(&empty_bar[stage], uint16_t(3)); else umma_commit(&empty_bar[stage]);
-          umma_commit(&tmem_full[buf]);
+          if (!kRowScale || kb == p.k_blocks - 1) umma_commit(&tmem_full[buf]);
         }
       }
     }
@@ -156,12 +162,72 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const int q4 = warp & 3;           // TMEM lane quarter this warp may access
     const int half = warp >> 2;        // which 128-column half of the 256-wide tile
     const uint32_t lane_addr = uint32_t(q4 * 32) << 16;
-    uint32_t it = 0;
+    uint32_t it = 0, tile_it = 0;
     for (int work = work_first; work < p.total_tiles; work += work_stride) {
       int m_tile, n_tile;
       tile_of(work, m_tile, n_tile);
       const int64_t col0 = int64_t(n_tile) * BN + half * 128;
       const bool half_active = col0 < p.n;
+      if (kRowScale) {
+        // ---- one epilogue per tile: c = T(float(acc) * a_s[row] * b_s[col] + bias[col])
+        const uint32_t buf = tile_it & 1u, bphase = (tile_it >> 1) & 1u;
+        ++tile_it;
+        const int64_t row0r = int64_t(m_tile) * BM + q4 * 32;
+        const int64_t rowr = row0r + lane;
+        const float sa = (rowr < p.m) ? __ldg(p.a_s + rowr) : 0.f;
+        const T* biasr = static_cast<const T*>(p.bias);
+        uint8_t* stager = c_stage + warp * kCStageBytes;
+        mbar_wait(&tmem_full[buf], bphase);
+        tc_fence_after_sync();
+        const uint32_t t0r = tmem_base + lane_addr + buf * BN + half * 128;
+#pragma unroll
+        for (int pass = 0; pass < 2; ++pass) {
+          const int64_t colp = col0 + pass * 64;
+          uint32_t r[64];
+          tmem_ld_x64(t0r + pass * 64, r);
+          tmem_ld_wait();
+          if (pass == 1) {  // all TMEM reads of this tile are done: hand the buffer back before the stores
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+          }
+#pragma unroll
+          for (int ch = 0; ch < 8; ++ch) {
+            uint32_t w[4];
+            float sb[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            uint32_t bw[4] = {0u, 0u, 0u, 0u};
+            if (half_active && colp + ch * 8 < p.n) {
+              const float4 s0 = __ldg(reinterpret_cast<const float4*>(p.b_s + colp + ch * 8));
+              const float4 s1 = __ldg(reinterpret_cast<const float4*>(p.b_s + colp + ch * 8) + 1);
+              sb[0] = s0.x; sb[1] = s0.y; sb[2] = s0.z; sb[3] = s0.w; sb[4] = s1.x; sb[5] = s1.y; sb[6] = s1.z; sb[7] = s1.w;
+              if (biasr != nullptr) {
+                const uint4 b4 = *reinterpret_cast<const uint4*>(biasr + colp + ch * 8);
+                bw[0] = b4.x; bw[1] = b4.y; bw[2] = b4.z; bw[3] = b4.w;
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float f0 = __int2float_rn(static_cast<int>(r[ch * 8 + 2 * j]));
+              const float f1 = __int2float_rn(static_cast<int>(r[ch * 8 + 2 * j + 1]));
+              const float y0 = __fadd_rn(__fmul_rn(__fmul_rn(f0, sa), sb[2 * j]), F16Traits<T>::lo(bw[j]));
+              const float y1 = __fadd_rn(__fmul_rn(__fmul_rn(f1, sa), sb[2 * j + 1]), F16Traits<T>::hi(bw[j]));
+              w[j] = F16Traits<T>::pack(y0, y1);
+            }
+            *reinterpret_cast<uint4*>(stager + lane * 128 + ((ch ^ (lane & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+          }
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rr = 4 * i + (lane >> 3), cc = lane & 7;
+            const uint4 v = *reinterpret_cast<const uint4*>(stager + rr * 128 + ((cc ^ (rr & 7)) << 4));
+            const int64_t grow = row0r + rr;
+            if (half_active && grow < p.m && colp + cc * 8 < p.n)
+              stg_v4(static_cast<T*>(p.c) + grow * p.n + colp + cc * 8, v);
+          }
+          __syncwarp();
+        }
+        continue;
+      }
       const float* as_row = p.a_s + int64_t(m_tile < p.m_tiles ? m_tile : p.m_tiles - 1) * p.k_blocks;  // odd tail pair
       const float* bs_row = p.b_s + (half_active ? (col0 >> 7) : 0) * p.k_blocks;
 
@@ -319,9 +385,9 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   }
 }
 
-template <typename T, bool kCluster>
+template <typename T, bool kCluster, bool kRowScale>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
-  auto kern = gemm_w8a8_kernel<T, kCluster>;
+  auto kern = gemm_w8a8_kernel<T, kCluster, kRowScale>;
   if (int rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemBytes)),
                           "cudaFuncSetAttribute(gemm_w8a8)"))
     return rc;
@@ -352,7 +418,8 @@ extern "C" int tdb200_gemm_w8a8(const int8_t* a_q, const float* a_s, const int8_
 }
 
 static int gemm_impl(const int8_t* a_q, const float* a_s, const int8_t* b_q, const float* b_s, const void* bias, void* c,
-                     int8_t* out_q, float* out_s, int c_dtype, int64_t m, int64_t n, int64_t k, int epilogue, void* stream);
+                     int8_t* out_q, float* out_s, int c_dtype, int64_t m, int64_t n, int64_t k, int epilogue, void* stream,
+                     bool row_scale = false);
 
 extern "C" int tdb200_gemm_w8a8_ex(const int8_t* a_q, const float* a_s, const int8_t* b_q, const float* b_s,
                                    const void* bias, void* c, int c_dtype, int64_t m, int64_t n, int64_t k,
@@ -369,8 +436,16 @@ extern "C" int tdb200_gemm_w8a8_quant_out(const int8_t* a_q, const float* a_s, c
   return gemm_impl(a_q, a_s, b_q, b_s, bias, out_q, out_q, out_s, mid_dtype, m, n, k, epilogue, stream);
 }
 
+extern "C" int tdb200_gemm_w8a8_rowwise(const int8_t* a_q, const float* a_s, const int8_t* b_q, const float* b_s,
+                                        const void* bias, void* c, int c_dtype, int64_t m, int64_t n, int64_t k,
+                                        void* stream) {
+  if (!c) return tdb::fail(TDB200_ERR_INVALID_ARG, "gemm_w8a8_rowwise: null pointer");
+  return gemm_impl(a_q, a_s, b_q, b_s, bias, c, nullptr, nullptr, c_dtype, m, n, k, TDB200_EPILOGUE_NONE, stream, true);
+}
+
 static int gemm_impl(const int8_t* a_q, const float* a_s, const int8_t* b_q, const float* b_s, const void* bias, void* c,
-                     int8_t* out_q, float* out_s, int c_dtype, int64_t m, int64_t n, int64_t k, int epilogue, void* stream) {
+                     int8_t* out_q, float* out_s, int c_dtype, int64_t m, int64_t n, int64_t k, int epilogue, void* stream,
+                     bool row_scale) {
   using namespace tdb;
   if (epilogue != TDB200_EPILOGUE_NONE && epilogue != TDB200_EPILOGUE_GELU_TANH)
     return fail(TDB200_ERR_INVALID_ARG, "gemm_w8a8_ex: unknown epilogue %d", epilogue);
@@ -414,9 +489,16 @@ static int gemm_impl(const int8_t* a_q, const float* a_s, const int8_t* b_q, con
   if (total > (int64_t(1) << 29)) return fail(TDB200_ERR_UNSUPPORTED, "gemm_w8a8: too many tiles");
   p.total_tiles = static_cast<int>(total);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (row_scale) {
+    if (k > 16384 * 8) return fail(TDB200_ERR_UNSUPPORTED, "gemm_w8a8_rowwise: k too large for int32 accumulation");
+    if (c_dtype == TDB200_DTYPE_BF16)
+      return use_cluster ? launch<__nv_bfloat16, true, true>(ta, tb, p, st) : launch<__nv_bfloat16, false, true>(ta, tb, p, st);
+    if (c_dtype == TDB200_DTYPE_FP16)
+      return use_cluster ? launch<__half, true, true>(ta, tb, p, st) : launch<__half, false, true>(ta, tb, p, st);
+  }
   if (c_dtype == TDB200_DTYPE_BF16)
-    return use_cluster ? launch<__nv_bfloat16, true>(ta, tb, p, st) : launch<__nv_bfloat16, false>(ta, tb, p, st);
+    return use_cluster ? launch<__nv_bfloat16, true, false>(ta, tb, p, st) : launch<__nv_bfloat16, false, false>(ta, tb, p, st);
   if (c_dtype == TDB200_DTYPE_FP16)
-    return use_cluster ? launch<__half, true>(ta, tb, p, st) : launch<__half, false>(ta, tb, p, st);
+    return use_cluster ? launch<__half, true, false>(ta, tb, p, st) : launch<__half, false, false>(ta, tb, p, st);
   return fail(TDB200_ERR_UNSUPPORTED, "gemm_w8a8: output dtype tag %d (bf16/fp16 only, gemm.cu:41-65)", c_dtype);
 }

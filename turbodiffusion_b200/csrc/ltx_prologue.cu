@@ -217,3 +217,80 @@ extern "C" int tdb200_ltx_split_rope(const void* x, const void* cos_freqs, const
     return fail(TDB200_ERR_UNSUPPORTED, "ltx_split_rope: dtype tag %d", dtype);
   return check_launch("ltx_split_rope_kernel");
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Per-row symmetric INT8 quantisation of the LTX W8A8 path (ltx_distillation/tilelang_w8a8.py:16-36):
+//   scale = max(amax, 1e-4) / 127;  q = clip(round_half_away(x / scale), -128, 127).   One CTA per row.
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+using namespace tdb;
+template <typename T, int kThreads, int kChunks>
+__global__ void __launch_bounds__(kThreads) row_quant_kernel(const T* __restrict__ x, int8_t* __restrict__ q,
+                                                             float* __restrict__ s, int n) {
+  __shared__ float red[kThreads / 32];
+  const int64_t row = blockIdx.x;
+  const int nchunks = n / 8;
+  uint4 raw[kChunks];
+  float amax = 0.f;
+#pragma unroll
+  for (int i = 0; i < kChunks; ++i) {
+    const int c = threadIdx.x + i * kThreads;
+    raw[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (c < nchunks) raw[i] = ldg_nc_v4(x + row * n + c * 8);
+    const uint32_t w[4] = {raw[i].x, raw[i].y, raw[i].z, raw[i].w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) amax = fmaxf(amax, fmaxf(fabsf(F16Traits<T>::lo(w[j])), fabsf(F16Traits<T>::hi(w[j]))));
+  }
+  amax = warp_max(amax);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = amax;
+  __syncthreads();
+#pragma unroll
+  for (int w = 0; w < kThreads / 32; ++w) amax = fmaxf(amax, red[w]);
+  const float scale = fmaxf(amax, 1.0e-4f) / 127.0f;
+  if (threadIdx.x == 0) s[row] = scale;
+#pragma unroll
+  for (int i = 0; i < kChunks; ++i) {
+    const int c = threadIdx.x + i * kThreads;
+    if (c >= nchunks) continue;
+    const uint32_t w[4] = {raw[i].x, raw[i].y, raw[i].z, raw[i].w};
+    uint32_t lo = 0, hi = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float v = (j & 1) ? F16Traits<T>::hi(w[j >> 1]) : F16Traits<T>::lo(w[j >> 1]);
+      const float sc = __fdiv_rn(v, scale);
+      float r = sc >= 0.f ? floorf(__fadd_rn(sc, 0.5f)) : ceilf(__fsub_rn(sc, 0.5f));
+      r = fminf(fmaxf(r, -128.f), 127.f);
+      const uint32_t b = static_cast<uint32_t>(static_cast<int>(r)) & 0xFFu;
+      if (j < 4) lo |= b << (8 * j); else hi |= b << (8 * (j - 4));
+    }
+    *reinterpret_cast<uint2*>(q + row * n + c * 8) = make_uint2(lo, hi);
+  }
+}
+}  // namespace
+
+extern "C" int tdb200_quant_int8_rowwise(const void* x, int dtype, int64_t m, int64_t k, int8_t* q, float* s, void* stream) {
+  using namespace tdb;
+  if (!x || !q || !s) return fail(TDB200_ERR_INVALID_ARG, "quant_int8_rowwise: null pointer");
+  if (m < 0 || k <= 0 || k % 8 != 0) return fail(TDB200_ERR_INVALID_ARG, "quant_int8_rowwise: bad shape (k %% 8 == 0)");
+  if (m == 0) return TDB200_OK;
+  if (!aligned16(x) || (reinterpret_cast<uintptr_t>(q) & 7u)) return fail(TDB200_ERR_INVALID_ARG, "quant_int8_rowwise: misaligned buffer");
+  if (m > 0x7FFFFFFFll) return fail(TDB200_ERR_UNSUPPORTED, "quant_int8_rowwise: too many rows");
+  if (int rc = require_sm100()) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int nchunks = static_cast<int>(k / 8);
+  const unsigned grid = static_cast<unsigned>(m);
+#define TDB_RQ(T, TH, CH) row_quant_kernel<T, TH, CH><<<grid, TH, 0, st>>>(static_cast<const T*>(x), q, s, static_cast<int>(k))
+#define TDB_RQ_DISPATCH(T)                         \
+  if (nchunks <= 128) TDB_RQ(T, 128, 1);           \
+  else if (nchunks <= 256) TDB_RQ(T, 128, 2);      \
+  else if (nchunks <= 512) TDB_RQ(T, 256, 2);      \
+  else if (nchunks <= 1024) TDB_RQ(T, 256, 4);     \
+  else if (nchunks <= 2048) TDB_RQ(T, 256, 8);     \
+  else return fail(TDB200_ERR_UNSUPPORTED, "quant_int8_rowwise: k too large")
+  if (dtype == TDB200_DTYPE_BF16) { TDB_RQ_DISPATCH(__nv_bfloat16); }
+  else if (dtype == TDB200_DTYPE_FP16) { TDB_RQ_DISPATCH(__half); }
+  else return fail(TDB200_ERR_UNSUPPORTED, "quant_int8_rowwise: dtype tag %d", dtype);
+#undef TDB_RQ_DISPATCH
+#undef TDB_RQ
+  return check_launch("row_quant_kernel");
+}

@@ -75,6 +75,7 @@ class SPAttention:
         self.sp, self.prims = sp, prims
         self._bufs = {}
         self._pending = None
+        self._pending_k = None
 
     def _gather_async(self, name: str, t: torch.Tensor):
         """t [1, rows, H, D] -> ([1, world*rows_pad, H, D] buffer, NCCL work handle); zero-padded tail of the last rank."""
@@ -92,11 +93,20 @@ class SPAttention:
     def _cdt(self, t):
         return self.prims.sla.dtype if hasattr(self.prims, "sla") else t.dtype
 
+    def start_k(self, k):
+        """K exists (projected, normalised, rotated): start its all-gather; the V and Q projections run under it."""
+        k = k.to(self._cdt(k)).contiguous()
+        k_full, wk = self._gather_async("k", k)
+        self._pending_k = (k, k_full, wk)
+
     def start_kv(self, k, v):
         sp = self.sp
         cdt = self._cdt(k)
-        k, v = k.to(cdt).contiguous(), v.to(cdt).contiguous()
-        k_full, wk = self._gather_async("k", k)
+        if getattr(self, "_pending_k", None) is None:
+            self.start_k(k)
+        k, k_full, wk = self._pending_k
+        self._pending_k = None
+        v = v.to(cdt).contiguous()
         v_full, wv = self._gather_async("v", v)
         kv, ksum = self.prims.moments(k, v)
         w1 = dist.all_reduce(kv, group=sp.group, async_op=True)

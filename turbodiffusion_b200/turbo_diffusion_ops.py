@@ -8,6 +8,8 @@ an implementation detail of the persistent tcgen05 kernel).
 """
 from __future__ import annotations
 
+import contextlib
+
 from typing import Optional, Tuple
 
 import torch
@@ -91,9 +93,10 @@ def gemm_cuda_quant_out(a_q, a_s, b_q, b_s, bias, mid_dtype, gelu: bool = False)
     s = torch.empty((_cdiv(m, 128), _cdiv(n, 128)), dtype=torch.float32, device=a_q.device)
     if bias is not None and bias.dtype != mid_dtype:
         bias = bias.to(mid_dtype)
-    check(lib().tdb200_gemm_w8a8_quant_out(ptr(a_q), ptr(a_s), ptr(b_q), ptr(b_s), ptr(bias), ptr(q), ptr(s),
-                                           DTYPE_TAG[mid_dtype], m, n, k, 1 if gelu else 0, stream_ptr(a_q.device)),
-          "gemm_cuda_quant_out")
+    with (GEMM_TIMER(m, n, k) if GEMM_TIMER is not None else contextlib.nullcontext()):
+        check(lib().tdb200_gemm_w8a8_quant_out(ptr(a_q), ptr(a_s), ptr(b_q), ptr(b_s), ptr(bias), ptr(q), ptr(s),
+                                               DTYPE_TAG[mid_dtype], m, n, k, 1 if gelu else 0, stream_ptr(a_q.device)),
+              "gemm_cuda_quant_out")
     return q, s
 
 
