@@ -201,6 +201,9 @@ def main():
     ap.add_argument("--layers", type=int, default=None, help="override the number of blocks (diagnostics only)")
     ap.add_argument("--topk", type=float, default=0.1)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--sp-mode", default="auto", choices=["auto", "allgather", "ulysses"],
+                    help="N>1 attention exchange: K/V all-gather + moment all-reduce, or head<->sequence all-to-all "
+                         "(needs heads %% N == 0); auto = the mode that measured faster (dist.py pick_mode)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile", action="store_true", help="device-resident region only (for runs under ncu)")
     ap.add_argument("--no-graph", action="store_true", help="time the eager (Python-launched) step instead of the CUDA graph")
@@ -234,7 +237,7 @@ def main():
     if world > 1:
         from turbodiffusion_b200.dist import SequenceParallel
         sp = SequenceParallel(L, world, rank)
-        sp.install(model)
+        sp_mode = sp.install(model, args.sp_mode)
         rows = sp.local_rows
         row0 = sp.row_begin
     else:
@@ -358,7 +361,7 @@ def main():
             "data": "synthetic",
             "config": {"workload": f"{shape['name']} DiT denoise step: {layers} blocks (SageSLA top-k {args.topk} + W8A8 + FastNorm)",
                        "L": L, "dim": dim, "heads": heads, "head_dim": d, "ffn": ffn, "text_len": text,
-                       "parallelism": f"sp{world}" if world > 1 else "single",
+                       "parallelism": f"sp{world}-{sp_mode}" if world > 1 else "single",
                        "l2": "activations per block exceed L2 (>=100 MB tensors, 30+ distinct weight sets)"},
             "e2e": {"value": FRAMES / (DENOISE_STEPS * ms_e2e * 1e-3), "unit": "frames/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": x_host.numel() * 2 + e0_host.numel() * 4 + ctx_host.numel() * 2,

@@ -13,7 +13,7 @@ import torch.multiprocessing as mp
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-from turbodiffusion_b200.dist import SequenceParallel, SPAttention, shard_rows  # noqa: E402
+from turbodiffusion_b200.dist import SequenceParallel, SPAttention, UlyssesAttention, shard_rows  # noqa: E402
 
 
 def test_shard_rows_are_128_aligned_and_cover_everything():
@@ -56,7 +56,7 @@ class OraclePrims:
         return (o_s + o_l).to(q.dtype).transpose(1, 2).contiguous()
 
 
-def _worker(rank, world, port, l, h, d, topk, out_path):
+def _worker(rank, world, port, l, h, d, topk, out_path, mode="allgather"):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -67,7 +67,17 @@ def _worker(rank, world, port, l, h, d, topk, out_path):
     v = torch.randn(1, l, h, d, generator=g).bfloat16()
     w, b = torch.randn(d, d, generator=g) * 0.05, torch.randn(d, generator=g) * 0.05
     sp = SequenceParallel(l, world, rank)
-    attn = SPAttention(sp, OraclePrims(O, w, b, topk))
+    if mode == "ulysses":
+        assert sp.pick_mode(h, "ulysses") == "ulysses"
+        class Prims:
+            @staticmethod
+            def attend(get_q, get_k, get_v):
+                kf, qf, vf = get_k(), get_q(), get_v()     # the order the GPU primitives consume them in
+                return O.sla_forward(qf, kf, vf, w, b, topk, mode="exact")
+        attn = UlyssesAttention(sp, Prims)
+        assert attn.q_first
+    else:
+        attn = SPAttention(sp, OraclePrims(O, w, b, topk))
     sl = slice(sp.row_begin, sp.row_end)
     out_local = attn(q[:, sl].contiguous(), k[:, sl].contiguous(), v[:, sl].contiguous())
     full = sp.gather_rows(out_local[0].reshape(sp.local_rows, h * d))
@@ -88,3 +98,27 @@ def test_sequence_parallel_attention_gloo_world2(tmp_path, l):
     mp.spawn(_worker, args=(2, port, l, 2, 64, 0.3, out), nprocs=2, join=True)
     res = torch.load(out)
     assert res["stats"]["rel_l2"] < 5e-3, res  # only bf16 output rounding differs from the single-process oracle
+
+
+@pytest.mark.parametrize("l", [600, 1000])
+def test_ulysses_attention_gloo_world2(tmp_path, l):
+    """Head<->sequence all-to-all mode (uneven row shards, 2 heads over 2 ranks): every head sees the whole sequence, so the
+    result is the single-process oracle's up to the CPU matmul's batch-shape-dependent summation order."""
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    out = str(tmp_path / "ul.pt")
+    mp.spawn(_worker, args=(2, port, l, 2, 64, 0.3, out, "ulysses"), nprocs=2, join=True)
+    res = torch.load(out)
+    assert res["stats"]["rel_l2"] < 1e-4, res
+
+
+def test_pick_mode():
+    sp = SequenceParallel(32760, world=8, rank=0)
+    assert sp.pick_mode(12) == "allgather" and sp.pick_mode(40) == "ulysses" and sp.pick_mode(40, "allgather") == "allgather"
+    with pytest.raises(ValueError):
+        sp.pick_mode(12, "ulysses")
+    assert SequenceParallel(32760, world=1, rank=0).pick_mode(12) == "allgather"
+    assert SequenceParallel(32760, world=2, rank=0).pick_mode(12) == "allgather"   # measured faster at N=2
+    assert SequenceParallel(32760, world=2, rank=0).pick_mode(12, "ulysses") == "ulysses"

@@ -11,7 +11,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, out_path):
+def _worker(rank, world, port, out_path, mode):
     sys.path.insert(0, ROOT)
     import torch.distributed as dist
     from turbodiffusion_b200.block import WanHotPath
@@ -31,7 +31,7 @@ def _worker(rank, world, port, out_path):
     model = WanHotPath(dim, ffn, heads, 2, dev, topk=0.4, seed=5)
     ref = model.step(x, e0, ang, ctx) if rank == 0 else None      # single-GPU result (no hook installed yet)
     sp = SequenceParallel(l, world, rank)
-    sp.install(model)
+    assert sp.install(model, mode) == mode
     y_local = model.step(sp.scatter(x), e0, sp.scatter(ang), ctx)
     y = sp.gather_rows(y_local)
     torch.cuda.synchronize()
@@ -43,7 +43,8 @@ def _worker(rank, world, port, out_path):
     dist.destroy_process_group()
 
 
-def test_sequence_parallel_matches_single_gpu(tmp_path):
+@pytest.mark.parametrize("mode", ["allgather", "ulysses"])
+def test_sequence_parallel_matches_single_gpu(tmp_path, mode):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
@@ -52,7 +53,7 @@ def test_sequence_parallel_matches_single_gpu(tmp_path):
     port = s.getsockname()[1]
     s.close()
     out = str(tmp_path / "sp.pt")
-    mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, port, out, mode), nprocs=2, join=True)
     res = torch.load(out)
-    # identical arithmetic per row; only the fp32 atomics order of the linear-attention moments differs
+    # identical arithmetic per row; only the fp32 atomics order of the linear-attention moments differs (both modes)
     assert res["rel_l2"] < 2e-3, res

@@ -90,8 +90,14 @@ class WanBlockB200:
             xq, xs = ops.layernorm_modulate_quant(x, e[1], e[0], eps)
         else:
             xq, xs = ops.layernorm_modulate_quant_from_stats(x, stats, e[1], e[0])
-        # K and V first: a sequence-parallel attention hook starts their all-gather while Q is still being produced
+        # K and V first: the all-gather hook starts their exchange while Q is still being produced.  The head<->sequence
+        # hook asks for Q first instead (its last exchange is hidden by the K/Q-side preparation, see dist.py).
         attn = self.attn_hook or self.sla
+        q = None
+        if getattr(attn, "q_first", False):
+            q = self._gemm(xq, xs, "self_attn.q", x.dtype)
+            q = ops.rmsnorm_rope(q, sd["self_attn.norm_q.weight"], angles, eps, h)
+            attn.start_q(q.view(1, l, h, d))
         k = self._gemm(xq, xs, "self_attn.k", x.dtype)
         k = ops.rmsnorm_rope(k, sd["self_attn.norm_k.weight"], angles, eps, h)
         if hasattr(attn, "start_k"):
@@ -99,8 +105,9 @@ class WanBlockB200:
         v = self._gemm(xq, xs, "self_attn.v", x.dtype)
         if hasattr(attn, "start_kv"):
             attn.start_kv(k.view(1, l, h, d), v.view(1, l, h, d))
-        q = self._gemm(xq, xs, "self_attn.q", x.dtype)
-        q = ops.rmsnorm_rope(q, sd["self_attn.norm_q.weight"], angles, eps, h)
+        if q is None:
+            q = self._gemm(xq, xs, "self_attn.q", x.dtype)
+            q = ops.rmsnorm_rope(q, sd["self_attn.norm_q.weight"], angles, eps, h)
         a = attn(q.view(1, l, h, d), k.view(1, l, h, d), v.view(1, l, h, d)).reshape(l, dim)
         y = self._linear(a, "self_attn.o")
         x = ops.gate_residual(x, y, e[2])  # x + y * e[2] (:405-406)

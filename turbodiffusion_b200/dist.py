@@ -15,7 +15,12 @@ all-gather pads it with zero rows at the very END of the sequence, so the gather
 by < 128*world padding rows that the kernels never read (lk = L).
 
 The reference's own scheme is Ulysses all-to-all (rcm/utils/a2a_cp.py:66-182; heads <-> sequence), which needs
-H % world == 0 (12 heads do not split 8 ways); it is not used by the inference scripts.
+H % world == 0 (12 heads do not split 8 ways).  UlyssesAttention below implements it as the second mode: three all-to-alls
+turn the local [rows, H, D] slabs of q, k, v into [L, H/world, D] (all rows, this rank's heads), the unchanged single-GPU SLA
+forward runs on those heads, and a fourth all-to-all brings the output back to [rows, H, D].  Per rank and layer it moves
+4*(N-1)/N^2 * L*dim*2 bytes instead of 2*(N-1)/N * L*dim*2 for the K/V all-gather (4x less at N = 8) and no rank repeats
+the K-side preparation of the full sequence; `SequenceParallel.install(mode="auto")` picks it where it measured faster
+(see pick_mode).
 """
 from __future__ import annotations
 
@@ -127,6 +132,105 @@ class SPAttention:
         return out.to(dtype)
 
 
+class UlyssesGpuPrims:
+    """Per-rank attention for the head<->sequence mode: the single-GPU SLA pipeline on this rank's heads, split so that each
+    stage starts as soon as the tensor it needs has arrived (K: key mean + INT8 + pooled means; Q: INT8 + pooled means +
+    block map; V: linear moments + fused attention)."""
+
+    def __init__(self, sla_module):
+        self.sla = sla_module
+
+    def attend(self, get_q, get_k, get_v):
+        from .SLA.core import attn_fwd, linear_moments
+        from .SLA.utils import QKPrep, block_map_from_pools, quant_k_into, quant_q_only
+        sla = self.sla
+        k = get_k()
+        d = k.shape[-1]
+        if d != 128:
+            return sla(get_q(), k, get_v())
+        kp = quant_k_into(QKPrep(), k, k.shape[1])
+        q = get_q()
+        prep = quant_q_only(q)
+        for f in ("kmean", "k_i8", "k_scale", "k_pool", "nblk"):
+            setattr(prep, f, getattr(kp, f))
+        topk = min(prep.nblk, int(sla.topk * prep.nblk))
+        _, lut = block_map_from_pools(prep.q_pool, prep.k_pool, topk)
+        v = get_v()
+        kv, ksum = linear_moments(k, v)
+        kvw = torch.matmul(sla.proj_l.weight.float(), kv).to(q.dtype).contiguous()
+        return attn_fwd(prep, v, q, lut, topk, kvw, ksum, sla.proj_l.bias.float().contiguous(), d ** -0.5)
+
+
+class UlyssesAttention:
+    """Head <-> sequence exchange (a2a_cp.py:66-182 semantics).  `q_first` asks the block to project Q before K and V and to
+    call start_q / start_k / start_kv as each tensor appears: the Q exchange then runs under the K and V projections, the K
+    exchange under the V projection, and the V exchange under the K- and Q-side preparation inside `prims.attend`, which
+    receives three callables that wait for and return the full-sequence [1, L, H/world, D] tensors.  The output goes back
+    to its rows with a fourth all-to-all.  Uneven shards use all_to_all_single's split sizes: no padding rows move."""
+
+    q_first = True
+
+    def __init__(self, sp: "SequenceParallel", prims, compute_dtype=None):
+        self.sp, self.prims, self.cdt = sp, prims, compute_dtype
+        self.rows_of = [shard_rows(sp.total_rows, sp.world, r)[1] - shard_rows(sp.total_rows, sp.world, r)[0]
+                        for r in range(sp.world)]
+        self._bufs = {}
+        self._pending = {}
+
+    def _buf(self, name, shape, like):
+        key = (name, tuple(shape), like.dtype, like.device)
+        if key not in self._bufs:
+            self._bufs[key] = torch.empty(*shape, dtype=like.dtype, device=like.device)
+        return self._bufs[key]
+
+    def _to_heads_async(self, name: str, t: torch.Tensor):
+        """t [1, rows, H, D] -> ([L, H/world, D] buffer, work handle)."""
+        sp, w = self.sp, self.sp.world
+        t = (t if self.cdt is None else t.to(self.cdt)).contiguous()
+        _, rows, h, d = t.shape
+        if h % w:
+            raise ValueError(f"Ulysses exchange needs heads % world == 0 (heads={h}, world={w})")
+        hl = h // w
+        send = self._buf(name + ".s", (w, rows, hl, d), t)
+        send.copy_(t[0].view(rows, w, hl, d).permute(1, 0, 2, 3))          # chunk j = head group j of my rows
+        recv = self._buf(name + ".r", (sp.total_rows, hl, d), t)
+        work = dist.all_to_all_single(recv, send.view(w * rows, hl, d), output_split_sizes=self.rows_of,
+                                      input_split_sizes=[rows] * w, group=sp.group, async_op=True)
+        self._pending[name] = (recv, work)
+
+    def start_q(self, q):
+        self._to_heads_async("q", q)
+
+    def start_k(self, k):
+        self._to_heads_async("k", k)
+
+    def start_kv(self, k, v):
+        if "k" not in self._pending:
+            self.start_k(k)
+        self._to_heads_async("v", v)
+
+    def _getter(self, name):
+        def get():
+            recv, work = self._pending.pop(name)
+            work.wait()
+            return recv.unsqueeze(0)
+        return get
+
+    def __call__(self, q, k, v):
+        sp, w = self.sp, self.sp.world
+        dtype = q.dtype
+        for name, t in (("q", q), ("k", k), ("v", v)):
+            if name not in self._pending:
+                self._to_heads_async(name, t)
+        o = self.prims.attend(self._getter("q"), self._getter("k"), self._getter("v"))       # [1, L, hl, D]
+        o = o[0].contiguous()
+        rows, hl, d = sp.local_rows, o.shape[1], o.shape[2]
+        recv = self._buf("o.r", (w, rows, hl, d), o)
+        dist.all_to_all_single(recv.view(w * rows, hl, d), o, output_split_sizes=[rows] * w,
+                               input_split_sizes=self.rows_of, group=sp.group)
+        return recv.permute(1, 0, 2, 3).reshape(1, rows, w * hl, d).to(dtype)            # chunk i = head group i of my rows
+
+
 class SequenceParallel:
     def __init__(self, total_rows: int, world: Optional[int] = None, rank: Optional[int] = None, group=None):
         self.group = group
@@ -138,11 +242,32 @@ class SequenceParallel:
         if self.local_rows <= 0:
             raise ValueError(f"rank {self.rank} owns no rows: L={total_rows} is too short for {self.world} ranks of 128-row blocks")
 
-    def install(self, model) -> None:
+    def pick_mode(self, heads: int, mode: str = "auto") -> str:
+        if mode not in ("auto", "allgather", "ulysses"):
+            raise ValueError(f"unknown sequence-parallel mode {mode!r}")
+        if mode == "auto":
+            # measured on B200 (profiles/r01_bench_*): at N=2 the all-gather mode is faster (shape A 75.8 vs 80.7 ms/step: equal
+            # bytes, but its exchanges hide under the Q projection while Ulysses has the output exchange and four slab
+            # permutes on the critical path); at N=8 Ulysses is (shape B 286.5 vs 346.0 ms/step: 4x fewer bytes and no
+            # rank repeats the full-sequence K preparation).  N=4 has not been measured yet and stays on all-gather.
+            return "ulysses" if self.world >= 8 and heads % self.world == 0 else "allgather"
+        if mode == "ulysses" and heads % self.world:
+            raise ValueError(f"mode 'ulysses' needs heads % world == 0 (heads={heads}, world={self.world})")
+        return mode
+
+    def install(self, model, mode: str = "auto") -> str:
         """Replace every block's attention callable by the sequence-parallel one (the reference seam is
-        `WanSelfAttention.attn_op.local_attn`, inference/modify_model.py:48-52)."""
+        `WanSelfAttention.attn_op.local_attn`, inference/modify_model.py:48-52).  Returns the mode used:
+        "allgather" (K/V all-gather + moment all-reduce, any head count) or "ulysses" (head<->sequence all-to-all)."""
+        used = None
         for blk in model.blocks:
-            blk.attn_hook = SPAttention(self, GpuPrimitives(blk.sla))
+            used = self.pick_mode(blk.heads, mode)
+            if used == "ulysses":
+                blk.attn_hook = UlyssesAttention(self, UlyssesGpuPrims(blk.sla), compute_dtype=blk.sla.dtype)
+            else:
+                blk.attn_hook = SPAttention(self, GpuPrimitives(blk.sla))
+        self.mode = used
+        return used
 
     def scatter(self, full: torch.Tensor) -> torch.Tensor:
         return full[self.row_begin:self.row_end].contiguous()
