@@ -192,8 +192,11 @@ int tdb200_ltx_split_rope(const void* x, const void* cos_freqs, const void* sin_
 
 /* LTX-2 W8A8 with per-row post-scale (ltx_distillation/tilelang_w8a8.py:16-36, 78-117):
  *   quant_int8_rowwise: x [m,k] 16-bit -> q int8 [m,k], s [m] fp32; scale = max(amax,1e-4)/127, round half away, clip.
- *   gemm_w8a8_rowwise:  c[i,j] = T( float(sum_k a_q[i,k]*b_q[j,k]) * a_s[i] * b_s[j] + bias[j] ), int32 accumulation over
- *                       all of K in TMEM, one epilogue per tile (no per-K-block dequant).  k % 128 == 0, n % 8 == 0. */
+ *                       (IEEE division here; the reference's Triton `/` is div.full.f32, so exact .5 ties may differ)
+ *   gemm_w8a8_rowwise:  c[i,j] = T( fma( float(sum_k a_q[i,k]*b_q[j,k]) * a_s[i], b_s[j], bias[j] ) ) -- the arithmetic the
+ *                       reference's TileLang epilogue executes (I2FP, FMUL, FFMA under nvcc's default -fmad; see
+ *                       tools/tilelang_epilogue_probe.py); int32 accumulation over all of K in TMEM, one epilogue per
+ *                       tile (no per-K-block dequant).  bias may be NULL (= 0).  k % 128 == 0, n % 8 == 0. */
 int tdb200_quant_int8_rowwise(const void* x, int dtype, int64_t m, int64_t k, int8_t* q, float* s, void* stream);
 int tdb200_gemm_w8a8_rowwise(const int8_t* a_q, const float* a_s, const int8_t* b_q, const float* b_s, const void* bias,
                              void* c, int c_dtype, int64_t m, int64_t n, int64_t k, void* stream);

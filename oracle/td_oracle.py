@@ -438,12 +438,15 @@ def ltx_row_quant_int8(x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
 
 
 def ltx_gemm_post_scale(a_q, a_s, b_q, b_s, bias, out_dtype=torch.bfloat16) -> torch.Tensor:
-    """tilelang_w8a8.py:108-114: C = int32_acc * sA[i] * sB[j] + bias[j] (fp32, left to right), cast to bf16."""
+    """tilelang_w8a8.py:108-114: C = int32_acc * sA[i] * sB[j] + bias[j], cast to bf16.  As executed on the GPU: TileLang
+    lowers the expression to `t = float(acc)*sA; u = t*sB; c = u + bias` and compiles it with nvcc's default -fmad, which
+    contracts the last two into one FFMA (64 I2FP + 64 FMUL + 64 FFMA per thread in the SASS, no FADD; reproduced by
+    tools/tilelang_epilogue_probe.py) -> c = fma(float(acc)*sA, sB, bias).  The fused multiply-add is evaluated in fp64
+    (the product of two fp32 values is exact there) and rounded once to fp32."""
     acc = (a_q.double() @ b_q.double().t())                       # exact integer accumulation (|sum| < 2^53)
-    f = acc.float()                                               # int32 -> fp32, round to nearest
-    y = (f * a_s[:, None]) * b_s[None, :]
-    if bias is not None:
-        y = y + bias.float()[None, :]
+    t = acc.float() * a_s[:, None]                                # I2FP (round to nearest), FMUL
+    b = torch.zeros(b_s.shape[0], dtype=torch.float64) if bias is None else bias.double()
+    y = (t.double() * b_s.double()[None, :] + b[None, :]).float()  # FFMA
     return y.to(out_dtype)
 
 

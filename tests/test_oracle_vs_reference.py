@@ -131,3 +131,29 @@ def test_dense_sdpa_equals_sparse_with_all_blocks():
     sp = O.sparse_attention(q, k, v, lut, 128, 64)
     de = O.dense_attention(q.float(), k.float(), v.float())
     assert O.stats(sp, de)["rel_l2"] < 1e-5
+
+
+@pytest.mark.parametrize("k", [384, 4096])
+def test_ltx_row_quant_matches_the_reference_triton_kernel(k):
+    """oracle.ltx_row_quant_int8 against the reference's own `_row_quant_kernel` (tilelang_w8a8.py:16-36) executed through
+    Triton's CPU interpreter (tools/make_golden.py ltx): zero row (1e-4 floor), exact .5 ties, outlier columns."""
+    g = torch.load(os.path.join(GOLD, f"ltx_rowquant_k{k}.pt"))
+    q, s = O.ltx_row_quant_int8(g["x"])
+    assert torch.equal(s, g["s"]) and torch.equal(q, g["q"])
+    assert g["q"][5, :8].tolist() == [127, 64, -64, 1, -1, 2, -2, 3]          # round half away from zero
+    assert g["s"][3].item() == pytest.approx(1e-4 / 127.0, rel=1e-6)
+
+
+def test_ltx_post_scale_epilogue_is_a_fused_multiply_add():
+    """The reference's TileLang epilogue executes fma(float(acc)*sA, sB, bias) (tools/tilelang_epilogue_probe.py,
+    profiles/r01_tilelang_epilogue_sass.txt).  Known answer where the fused and the unfused evaluation differ:
+    (1+2^-12)(1+3*2^-12) = 1 + 2^-10 + 3*2^-24 is a rounding tie for a separate multiply (-> 1 + 2^-10 + 2^-22); with
+    bias = -(1+2^-10) the unfused result is 4*2^-24, the fused one keeps 3*2^-24."""
+    a_q = torch.tensor([[1] + [0] * 127], dtype=torch.int8)
+    b_q = torch.tensor([[1] + [0] * 127], dtype=torch.int8)
+    a_s = torch.tensor([1.0 + 2.0 ** -12])
+    b_s = torch.tensor([1.0 + 3 * 2.0 ** -12])
+    bias = torch.tensor([-(1.0 + 2.0 ** -10)]).half()
+    y = O.ltx_gemm_post_scale(a_q, a_s, b_q, b_s, bias, out_dtype=torch.float32)
+    assert y.item() == 3 * 2.0 ** -24
+    assert ((a_s * b_s) + bias.float()).item() == 4 * 2.0 ** -24      # what an unfused mul + add would return

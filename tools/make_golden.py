@@ -1,6 +1,6 @@
 """Generate tests/golden/*.pt by running the REFERENCE's own code on CPU (this container only).
 
-  TRITON_INTERPRET=1 python tools/make_golden.py
+  TRITON_INTERPRET=1 python tools/make_golden.py [norm] [sla] [ltx]     (no names = all; each group reseeds itself)
 
 Imports /root/reference/turbodiffusion (ops/core.py Triton norms, SLA/utils.py, SLA/kernel.py, SLA/core.py) with a stub
 for the CUDA-only pybind module, runs the Triton kernels through Triton's CPU interpreter and stores small seeded
@@ -69,6 +69,12 @@ torch.amp.autocast = lambda device_type, dtype=None, **kw: _orig_autocast("cpu",
 
 os.makedirs(OUT, exist_ok=True)
 torch.manual_seed(20260922)
+ONLY = set(sys.argv[1:])
+
+
+def want(group):
+    return not ONLY or group in ONLY
+
 
 
 def save(name, **kw):
@@ -77,7 +83,7 @@ def save(name, **kw):
 
 
 # ---- norms (ops/core.py Triton kernels), N not a power of two exposes the variance padding behaviour
-for n in (1536, 5120, 256):
+for n in ((1536, 5120, 256) if want("norm") else ()):
     rows = 32 if n <= 512 else 6  # the reference kernels do not mask rows when N <= 512 (BLOCK_M = 32): keep M % 32 == 0
     x = (torch.randn(rows, n) * 1.3 + 0.8).bfloat16()
     w = torch.rand(n) + 0.5
@@ -89,7 +95,7 @@ for n in (1536, 5120, 256):
     save(f"norm_n{n}", x=x, w=w, b=b, rms=rms, ln=ln, ln_aff=ln_aff, ln_f32=ln_f32, eps=1e-6)
 
 # ---- block map + Triton sparse attention + full SparseLinearAttention.forward
-for tag, (bsz, h, l, d, topk) in {"sla_a": (1, 2, 600, 128, 0.25), "sla_b": (2, 1, 333, 64, 0.5)}.items():
+for tag, (bsz, h, l, d, topk) in ({"sla_a": (1, 2, 600, 128, 0.25), "sla_b": (2, 1, 333, 64, 0.5)}.items() if want("sla") else ()):
     q = torch.randn(bsz, l, h, d).bfloat16()
     k = (torch.randn(bsz, l, h, d) + torch.randn(1, 1, h, d) * 2.0).bfloat16()  # per-channel key bias: smooth-K matters
     v = torch.randn(bsz, l, h, d).bfloat16()
@@ -108,3 +114,25 @@ for tag, (bsz, h, l, d, topk) in {"sla_a": (1, 2, 600, 128, 0.25), "sla_b": (2, 
     save(tag, q=q, k=k, v=v, pooled_q=pooled_q, pooled_k=pooled_k, score=score, sparse_map=sparse_map, lut=lut,
          topk=real_topk, topk_ratio=topk, proj_w=mod.proj_l.weight.detach().clone(),
          proj_b=mod.proj_l.bias.detach().clone(), o_s=o_s, out=out)
+
+# ---- LTX per-row INT8 quantisation (TurboT2AV ltx_distillation/tilelang_w8a8.py:16-36), the Triton kernel itself
+if want("ltx"):
+    import importlib.util
+    torch.manual_seed(20260923)
+    spec = importlib.util.spec_from_file_location(
+        "ref_tilelang_w8a8", "/root/reference/TurboT2AV/LTX-2/packages/ltx-distillation/src/ltx_distillation/tilelang_w8a8.py")
+    ref_tl = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref_tl)
+    import triton
+    for k in (384, 4096):
+        m = 12
+        x = (torch.randn(m, k) * 1.7).bfloat16()
+        x[:, ::97] *= 9.0                       # outlier columns
+        x[3] = 0                                # amax below the 1e-4 floor
+        x[4] = x[4].abs().clamp_min(0.01)       # all positive
+        x[5, :8] = torch.tensor([127.0, 63.5, -63.5, 0.5, -0.5, 1.5, -1.5, 2.5]).bfloat16()   # exact .5 ties at scale 1
+        x[5, 8:] = x[5, 8:].clamp(-100, 100)
+        q = torch.empty(m, k, dtype=torch.int8)
+        sc = torch.empty(m, dtype=torch.float32)
+        ref_tl._row_quant_kernel[(m,)](x, q, sc, k, triton.next_power_of_2(k))     # body of row_quant_int8 (:39-52)
+        save(f"ltx_rowquant_k{k}", x=x, q=q, s=sc)

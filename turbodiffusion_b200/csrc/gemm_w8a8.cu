@@ -169,7 +169,8 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const int64_t col0 = int64_t(n_tile) * BN + half * 128;
       const bool half_active = col0 < p.n;
       if (kRowScale) {
-        // ---- one epilogue per tile: c = T(float(acc) * a_s[row] * b_s[col] + bias[col])
+        // ---- one epilogue per tile: c = T(fma(float(acc) * a_s[row], b_s[col], bias[col])): the reference's TileLang
+        //      epilogue compiles (nvcc default -fmad) to I2FP, FMUL, FFMA per element (tools/tilelang_epilogue_probe.py)
         const uint32_t buf = tile_it & 1u, bphase = (tile_it >> 1) & 1u;
         ++tile_it;
         const int64_t row0r = int64_t(m_tile) * BM + q4 * 32;
@@ -209,8 +210,8 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             for (int j = 0; j < 4; ++j) {
               const float f0 = __int2float_rn(static_cast<int>(r[ch * 8 + 2 * j]));
               const float f1 = __int2float_rn(static_cast<int>(r[ch * 8 + 2 * j + 1]));
-              const float y0 = __fadd_rn(__fmul_rn(__fmul_rn(f0, sa), sb[2 * j]), F16Traits<T>::lo(bw[j]));
-              const float y1 = __fadd_rn(__fmul_rn(__fmul_rn(f1, sa), sb[2 * j + 1]), F16Traits<T>::hi(bw[j]));
+              const float y0 = __fmaf_rn(__fmul_rn(f0, sa), sb[2 * j], F16Traits<T>::lo(bw[j]));
+              const float y1 = __fmaf_rn(__fmul_rn(f1, sa), sb[2 * j + 1], F16Traits<T>::hi(bw[j]));
               w[j] = F16Traits<T>::pack(y0, y1);
             }
             *reinterpret_cast<uint4*>(stager + lane * 128 + ((ch ^ (lane & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
