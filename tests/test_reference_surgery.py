@@ -68,3 +68,44 @@ def test_unmodified_reference_surgery_builds_the_same_interface():
     assert ours["topk"] == ref["topk"] and ours["proj_l_zero"] and ref["proj_l_zero"]    # SLA/core.py:163-166 zero init
     quant_keys = [k for k in ours["state"] if k.endswith("int8_weight")]
     assert len(quant_keys) == 2 * 10                                                     # 10 linears per block, proj_l skipped
+
+
+LTX_SCRIPT = r'''
+import json, sys
+sys.path.insert(0, sys.argv[1])
+import torch
+import turbodiffusion_b200
+turbodiffusion_b200.install()
+base = sys.argv[2]
+for p in ("ltx-distillation/src", "ltx-core/src", "ltx-pipelines/src", "ltx-trainer/src"):
+    sys.path.insert(0, base + "/" + p)
+import ltx_distillation.acceleration as acc
+ops = acc._td_w8a8_ops()                                   # acceleration.py:690-703
+model = torch.nn.Sequential(torch.nn.RMSNorm(64, eps=1e-6), torch.nn.LayerNorm(64, eps=1e-6))
+n_norm = acc.replace_ltx_norms(model)                      # acceleration.py:619-635
+sage = acc.LTXSageSLAAttention(head_dim=128, topk=0.3, use_bf16=True)      # acceleration.py:226-240
+sla = acc.LTXSLAAttention(head_dim=64, topk=0.3, block_q=128, block_k=64, use_bf16=True)
+print("RESULT" + json.dumps({
+    "ops": [f.__module__ + "." + f.__name__ for f in ops], "n_norm": n_norm,
+    "norm_types": [type(m).__module__ + "." + type(m).__name__ for m in model],
+    "sage": type(sage.local_attn).__module__, "sla": type(sla.local_attn).__module__,
+    "sage_state": sorted(sage.state_dict().keys())}))
+'''
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/TurboT2AV/LTX-2/packages"), reason="build container only")
+def test_ltx_acceleration_backend_resolves_to_this_package():
+    """The LTX-2 client (TurboT2AV ltx_distillation/acceleration.py) looks the W8A8 / FastNorm / SLA operators up by name
+    at run time; with install() every lookup must land in turbodiffusion_b200 (incl. the gemm_cuda_swizzle* exports the
+    reference snapshot's own extension lacks)."""
+    p = subprocess.run([sys.executable, "-c", LTX_SCRIPT, ROOT, "/root/reference/TurboT2AV/LTX-2/packages"],
+                       capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stderr[-3000:]
+    r = json.loads([ln for ln in p.stdout.splitlines() if ln.startswith("RESULT")][-1][len("RESULT"):])
+    assert r["ops"] == ["turbodiffusion_b200.ops.core.int8_quant", "turbodiffusion_b200.turbo_diffusion_ops.quant_cuda",
+                        "turbodiffusion_b200.turbo_diffusion_ops.gemm_cuda_swizzle",
+                        "turbodiffusion_b200.turbo_diffusion_ops.gemm_cuda_swizzle_bias"]
+    assert r["n_norm"] == 2 and r["norm_types"] == ["turbodiffusion_b200.ops.core.FastRMSNorm",
+                                                     "turbodiffusion_b200.ops.core.FastLayerNorm"]
+    assert r["sage"].startswith("turbodiffusion_b200") and r["sla"].startswith("turbodiffusion_b200")
+    assert r["sage_state"] == ["local_attn.proj_l.bias", "local_attn.proj_l.weight"]
