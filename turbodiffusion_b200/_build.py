@@ -26,6 +26,12 @@ NVCC_FLAGS = [
 ]
 
 
+def _extra_defines():
+    """Experiment switches for kernel variants (e.g. TDB200_NVCC_DEFINES="-DTDB_GEMM_CVT_MIX=1"); unset = the shipped kernels.
+    Changing it needs --force (object staleness only tracks source mtimes)."""
+    return os.environ.get("TDB200_NVCC_DEFINES", "").split()
+
+
 def _nvcc() -> str:
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
@@ -53,7 +59,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     for src in sources():
         obj = os.path.join(BUILD, src[:-3] + ".o")
         if force or _stale(obj, [os.path.join(CSRC, src)] + headers):
-            cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-I", INCLUDE, "-c",
+            cmd = [nvcc] + NVCC_FLAGS + _extra_defines() + (["-Xptxas", "-v"] if verbose else []) + ["-I", INCLUDE, "-c",
                                                                                   os.path.join(CSRC, src), "-o", obj]
             jobs.append((src, cmd))
     if jobs:
