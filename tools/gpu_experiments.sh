@@ -25,6 +25,8 @@ PY
 }
 variant gemm_base    gemm_w8a8.cu ""                         "tests/test_gpu_quant_gemm.py tests/test_gpu_vs_reference_ext.py" "gemm_w8a8/"
 variant gemm_cvtmix  gemm_w8a8.cu "-DTDB_GEMM_CVT_MIX=1"     "tests/test_gpu_quant_gemm.py tests/test_gpu_vs_reference_ext.py" "gemm_w8a8/"
+variant gemm_ldpipe  gemm_w8a8.cu "-DTDB_GEMM_LD_PIPE=1"     "tests/test_gpu_quant_gemm.py tests/test_gpu_vs_reference_ext.py" "gemm_w8a8/"
+variant gemm_ldpipe_cvtmix gemm_w8a8.cu "-DTDB_GEMM_LD_PIPE=1 -DTDB_GEMM_CVT_MIX=1" "tests/test_gpu_quant_gemm.py tests/test_gpu_vs_reference_ext.py" "gemm_w8a8/"
 variant attn_base    sla_attn.cu  ""                         "tests/test_gpu_sla.py -k forward"                                "attn_sweep"
 variant attn_poly    sla_attn.cu  "-DTDB_ATTN_POLY_EXP2=1"   "tests/test_gpu_sla.py -k forward"                                "attn_sweep"
 touch turbodiffusion_b200/csrc/gemm_w8a8.cu turbodiffusion_b200/csrc/sla_attn.cu

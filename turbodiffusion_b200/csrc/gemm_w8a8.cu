@@ -28,6 +28,9 @@
 #ifndef TDB_GEMM_CVT_MIX
 #define TDB_GEMM_CVT_MIX 0
 #endif
+#ifndef TDB_GEMM_LD_PIPE
+#define TDB_GEMM_LD_PIPE 0
+#endif
 
 namespace {
 
@@ -256,6 +259,40 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         mbar_wait(&tmem_full[buf], bphase);
         tc_fence_after_sync();
         const uint32_t t0 = tmem_base + lane_addr + buf * BN + half * 128;
+#if TDB_GEMM_LD_PIPE
+        // Experiment (off by default): four 32-column chunks, the load of chunk c+1 is issued before chunk c is converted,
+        // so the TMEM read latency overlaps the I2FP/FFMA work of the same warp (128 + 2*32 live registers instead of 128 + 64).
+        {
+          uint32_t ra[32], rb[32];
+          auto dq32 = [&](uint32_t (&r)[32], int base) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+              const bool xu = TDB_GEMM_CVT_MIX && ((j >> 1) % 5) == 4;  // see the CVT_MIX note below
+              const float f0 = xu ? __int2float_rd(static_cast<int>(r[j])) : __int2float_rn(static_cast<int>(r[j]));
+              const float f1 = xu ? __int2float_rd(static_cast<int>(r[j + 1])) : __int2float_rn(static_cast<int>(r[j + 1]));
+              const float2 a = __ffma2_rn(make_float2(f0, f1), make_float2(scale, scale), make_float2(acc[base + j], acc[base + j + 1]));
+              acc[base + j] = a.x;
+              acc[base + j + 1] = a.y;
+            }
+          };
+          tmem_ld_x32(t0, ra);
+          tmem_ld_wait();
+          tmem_ld_x32(t0 + 32, rb);
+          reg_fence_x32(ra);
+          dq32(ra, 0);
+          tmem_ld_wait();
+          tmem_ld_x32(t0 + 64, ra);
+          reg_fence_x32(rb);
+          dq32(rb, 32);
+          tmem_ld_wait();
+          tmem_ld_x32(t0 + 96, rb);
+          reg_fence_x32(ra);
+          dq32(ra, 64);
+          tmem_ld_wait();
+          reg_fence_x32(rb);
+          dq32(rb, 96);
+        }
+#else
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
           uint32_t r[64];
@@ -282,6 +319,7 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             acc[c * 64 + j] = fmaf(__int2float_rn(static_cast<int>(r[j])), scale, acc[c * 64 + j]);
 #endif
         }
+#endif  // TDB_GEMM_LD_PIPE
         tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tmem_empty[buf]);
