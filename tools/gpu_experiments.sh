@@ -9,7 +9,7 @@ variant() {  # name  source  defines  pytest-args  microbench-filter
   local name=$1 src=$2 defs=$3 tests=$4 filt=$5
   touch turbodiffusion_b200/csrc/$src
   TDB200_NVCC_DEFINES="$defs" python -m turbodiffusion_b200._build > gpurun_out/exp_${name}_build.log 2>&1 || { echo "$name: build failed"; return; }
-  timeout 400 python -m pytest $tests -x -q -m gpu > gpurun_out/exp_${name}_tests.log 2>&1
+  timeout 240 python -m pytest $tests -x -q -m gpu > gpurun_out/exp_${name}_tests.log 2>&1
   echo "== $name tests rc=$? $(tail -n 1 gpurun_out/exp_${name}_tests.log)"
   if [ "$filt" = "attn_sweep" ]; then   # fused attention: time vs selected key blocks + the softmax-warp phase trace
     timeout 400 python tools/attn_sweep.py 2>/dev/null | grep '^{' > gpurun_out/exp_${name}_mb.jsonl
@@ -29,5 +29,7 @@ variant gemm_ldpipe  gemm_w8a8.cu "-DTDB_GEMM_LD_PIPE=1"     "tests/test_gpu_qua
 variant gemm_ldpipe_cvtmix gemm_w8a8.cu "-DTDB_GEMM_LD_PIPE=1 -DTDB_GEMM_CVT_MIX=1" "tests/test_gpu_quant_gemm.py tests/test_gpu_vs_reference_ext.py" "gemm_w8a8/"
 variant attn_base    sla_attn.cu  ""                         "tests/test_gpu_sla.py -k forward"                                "attn_sweep"
 variant attn_poly    sla_attn.cu  "-DTDB_ATTN_POLY_EXP2=1"   "tests/test_gpu_sla.py -k forward"                                "attn_sweep"
+variant attn_ptmem   sla_attn.cu  "-DTDB_ATTN_P_TMEM=1"      "tests/test_gpu_sla.py -k forward"                                "attn_sweep"
+variant attn_ptmem_poly sla_attn.cu "-DTDB_ATTN_P_TMEM=1 -DTDB_ATTN_POLY_EXP2=1" "tests/test_gpu_sla.py -k forward"                       "attn_sweep"
 touch turbodiffusion_b200/csrc/gemm_w8a8.cu turbodiffusion_b200/csrc/sla_attn.cu
 python -m turbodiffusion_b200._build > gpurun_out/exp_restore_build.log 2>&1 && echo "default build restored"

@@ -226,6 +226,18 @@ __device__ __forceinline__ void umma_f16_ss(uint32_t d_tmem, uint64_t a_desc, ui
       : "memory");
 }
 
+// A operand read from tensor memory (the ".ts" form): lane = row of A, each 32-bit column holds two consecutive K elements
+// (low half = even k).  a_tmem addresses the first column; a K=16 step of a 16-bit type advances it by 8 columns.
+__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 // ------------------------------------------------------------------------------------------
 // tcgen05: TMEM <-> registers.  32x32b shape: thread t of the warp owns lane (32*(warp%4) + t),
 // register j holds column (base_col + j).  taddr = (lane << 16) | column.

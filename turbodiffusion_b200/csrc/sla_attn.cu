@@ -29,6 +29,13 @@
 #ifndef TDB_ATTN_POLY_EXP2
 #define TDB_ATTN_POLY_EXP2 0
 #endif
+// -DTDB_ATTN_P_TMEM=1: P(j) is written with tcgen05.st into the first 32 columns of the S buffer it was computed from
+// (S(j) already lives in registers) and P.V reads its A operand from tensor memory (tcgen05.mma [d], [a_tmem], b_desc).
+// That removes the 16 KB st.shared + fence.proxy.async publish and the wait for the single smem P buffer; the in-order
+// tensor pipe keeps Q.K^T(j+2) behind P.V(j), which is what makes the aliasing safe (the MMA warp issues P.V(j) first).
+#ifndef TDB_ATTN_P_TMEM
+#define TDB_ATTN_P_TMEM 0
+#endif
 
 namespace {
 #if TDB_ATTN_POLY_EXP2
@@ -202,12 +209,19 @@ sla_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q8, const __grid_co
         mbar_wait(&bars[kBarPFull], i & 1);
         mbar_wait(&bars[kBarVFull + st], (i / kStages) & 1);
         tc_fence_after_sync();
-        const uint64_t pdesc = make_desc_kmajor_sw128(sbase + kOffP);
         const uint64_t vdesc = make_desc_mnmajor_sw128(sbase + kOffV + st * kVBytes, kVBytes / 2);
+#if TDB_ATTN_P_TMEM
+#pragma unroll
+        for (int ks = 0; ks < BLKK / 16; ++ks)  // K=16 keys per MMA: P +8 TMEM columns, V +16 rows (2048 B)
+          umma_f16_ts(tmem_base + kColO, tmem_base + kColS + uint32_t(i & 1) * BLKK + uint32_t(ks * 8),
+                      vdesc + uint64_t(ks * 128), id_pv, (i > 0 || ks > 0) ? 1u : 0u);
+#else
+        const uint64_t pdesc = make_desc_kmajor_sw128(sbase + kOffP);
 #pragma unroll
         for (int ks = 0; ks < BLKK / 16; ++ks)  // K=16 keys per MMA: P +32 B in its row, V +16 rows (2048 B)
           umma_f16_ss(tmem_base + kColO, pdesc + uint64_t(ks * 2), vdesc + uint64_t(ks * 128), id_pv,
                       (i > 0 || ks > 0) ? 1u : 0u);
+#endif
         umma_commit(&bars[kBarVEmpty + st]);
         umma_commit(&bars[kBarPEmpty]);
         umma_commit(&bars[kBarPvDone]);
@@ -385,6 +399,15 @@ sla_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q8, const __grid_co
         tmem_ld_x32(tn + 32, s1);
       }
 
+#if TDB_ATTN_P_TMEM
+      // ---- P row -> tensor memory: 32 packed columns over the S buffer this block was read from (double-buffered with S)
+      TDB_TRACE(tracing, j, 5);
+      tmem_st_x32(tmem_base + lane_addr + kColS + uint32_t(st) * BLKK, pw);
+      tmem_st_wait();
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars[kBarPFull]);
+#else
       // ---- P row -> shared memory, K-major SW128: 16-byte chunk c of row r lives at r*128 + ((c ^ (r & 7)) << 4)
       mbar_wait(&bars[kBarPEmpty], (j & 1) ^ 1);     // P.V of block j-1 has finished reading the (single) P buffer
       TDB_TRACE(tracing, j, 5);
@@ -396,6 +419,7 @@ sla_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q8, const __grid_co
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars[kBarPFull]);
+#endif
       TDB_TRACE(tracing, j, 6);
     }
     if (tracing) trace_base[63 * 8 + 7] = clock64();  // loop exit
