@@ -13,7 +13,8 @@ import torch.multiprocessing as mp
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-from turbodiffusion_b200.dist import SequenceParallel, SPAttention, UlyssesAttention, shard_rows  # noqa: E402
+from turbodiffusion_b200.dist import (SequenceParallel, SPAttention, UlyssesAttention, UnevenUlyssesAttention,  # noqa: E402
+                                      shard_rows, split_heads)
 
 
 def test_shard_rows_are_128_aligned_and_cover_everything():
@@ -74,7 +75,7 @@ def _worker(rank, world, port, l, h, d, topk, out_path, mode="allgather"):
             def attend(get_q, get_k, get_v):
                 kf, qf, vf = get_k(), get_q(), get_v()     # the order the GPU primitives consume them in
                 return O.sla_forward(qf, kf, vf, w, b, topk, mode="exact")
-        attn = UlyssesAttention(sp, Prims)
+        attn = UlyssesAttention(sp, Prims) if h % world == 0 else UnevenUlyssesAttention(sp, Prims, h)
         assert attn.q_first
     else:
         attn = SPAttention(sp, OraclePrims(O, w, b, topk))
@@ -114,11 +115,31 @@ def test_ulysses_attention_gloo_world2(tmp_path, l):
     assert res["stats"]["rel_l2"] < 1e-4, res
 
 
+@pytest.mark.parametrize("l,h", [(600, 3), (1000, 5)])
+def test_uneven_ulysses_attention_gloo_world2(tmp_path, l, h):
+    """heads % world != 0: rank 0 takes the extra head (3 heads -> 2+1, 5 -> 3+2), uneven row shards at the same time."""
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    out = str(tmp_path / "ul.pt")
+    mp.spawn(_worker, args=(2, port, l, h, 64, 0.3, out, "ulysses"), nprocs=2, join=True)
+    res = torch.load(out)
+    assert res["stats"]["rel_l2"] < 1e-4, res
+
+
+def test_split_heads():
+    assert split_heads(12, 8) == ([2, 2, 2, 2, 1, 1, 1, 1], [0, 2, 4, 6, 8, 9, 10, 11])
+    assert split_heads(40, 8) == ([5] * 8, list(range(0, 40, 5)))
+    assert split_heads(3, 2) == ([2, 1], [0, 2])
+
+
 def test_pick_mode():
     sp = SequenceParallel(32760, world=8, rank=0)
     assert sp.pick_mode(12) == "allgather" and sp.pick_mode(40) == "ulysses" and sp.pick_mode(40, "allgather") == "allgather"
+    assert sp.pick_mode(12, "ulysses") == "ulysses"          # uneven head split (opt-in)
     with pytest.raises(ValueError):
-        sp.pick_mode(12, "ulysses")
+        sp.pick_mode(4, "ulysses")                             # fewer heads than ranks
     assert SequenceParallel(32760, world=1, rank=0).pick_mode(12) == "allgather"
     assert SequenceParallel(32760, world=2, rank=0).pick_mode(12) == "allgather"   # measured faster at N=2
     assert SequenceParallel(32760, world=2, rank=0).pick_mode(12, "ulysses") == "ulysses"

@@ -11,7 +11,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, out_path, mode):
+def _worker(rank, world, port, out_path, mode, dim, heads):
     sys.path.insert(0, ROOT)
     import torch.distributed as dist
     from turbodiffusion_b200.block import WanHotPath
@@ -21,7 +21,7 @@ def _worker(rank, world, port, out_path, mode):
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
-    dim, heads, ffn, thw = 256, 2, 512, (3, 10, 23)  # L = 690 -> 6 blocks of 128: ranks get 384 and 306 rows
+    ffn, thw = 512, (3, 10, 23)  # L = 690 -> 6 blocks of 128: ranks get 384 and 306 rows
     l = thw[0] * thw[1] * thw[2]
     g = torch.Generator().manual_seed(11)
     x = torch.randn(l, dim, generator=g).bfloat16().to(dev)
@@ -43,8 +43,9 @@ def _worker(rank, world, port, out_path, mode):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("mode", ["allgather", "ulysses"])
-def test_sequence_parallel_matches_single_gpu(tmp_path, mode):
+@pytest.mark.parametrize("mode,dim,heads", [("allgather", 256, 2), ("ulysses", 256, 2), ("allgather", 384, 3),
+                                            ("ulysses", 384, 3)])     # 3 heads over 2 ranks: the uneven head split
+def test_sequence_parallel_matches_single_gpu(tmp_path, mode, dim, heads):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
@@ -53,7 +54,7 @@ def test_sequence_parallel_matches_single_gpu(tmp_path, mode):
     port = s.getsockname()[1]
     s.close()
     out = str(tmp_path / "sp.pt")
-    mp.spawn(_worker, args=(2, port, out, mode), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, port, out, mode, dim, heads), nprocs=2, join=True)
     res = torch.load(out)
     # identical arithmetic per row; only the fp32 atomics order of the linear-attention moments differs (both modes)
     assert res["rel_l2"] < 2e-3, res

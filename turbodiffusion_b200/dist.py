@@ -231,6 +231,65 @@ class UlyssesAttention:
         return recv.permute(1, 0, 2, 3).reshape(1, rows, w * hl, d).to(dtype)            # chunk i = head group i of my rows
 
 
+def split_heads(heads: int, world: int):
+    """Contiguous head ranges per rank, the first heads % world ranks get one more: returns (counts, offsets)."""
+    counts = [heads // world + (1 if r < heads % world else 0) for r in range(world)]
+    offsets = [sum(counts[:r]) for r in range(world)]
+    return counts, offsets
+
+
+class UnevenUlyssesAttention(UlyssesAttention):
+    """The same exchange when heads % world != 0 (e.g. the 12 heads of Wan-1.3B on 8 GPUs -> 2,2,2,2,1,1,1,1): rank r takes
+    the contiguous head range split_heads() assigns it; every all-to-all uses per-peer split sizes in units of one
+    [D]-row (rows * heads_of_peer).  Opt-in (`mode="ulysses"`); validated on CPU (gloo), not yet timed on GPUs."""
+
+    def __init__(self, sp: "SequenceParallel", prims, heads: int, compute_dtype=None):
+        super().__init__(sp, prims, compute_dtype)
+        if heads < sp.world:
+            raise ValueError(f"Ulysses exchange needs at least one head per rank (heads={heads}, world={sp.world})")
+        self.heads = heads
+        self.heads_of, self.head_off = split_heads(heads, sp.world)
+
+    def _to_heads_async(self, name: str, t: torch.Tensor):
+        """t [1, rows, H, D] -> ([L, heads_of[rank], D] buffer, work handle)."""
+        sp, w = self.sp, self.sp.world
+        t = (t if self.cdt is None else t.to(self.cdt)).contiguous()
+        _, rows, h, d = t.shape
+        if h != self.heads:
+            raise ValueError(f"expected {self.heads} heads, got {h}")
+        send = self._buf(name + ".s", (rows * h, d), t)
+        pos = 0
+        for j in range(w):                                                  # chunk j = rank j's heads of my rows
+            n = rows * self.heads_of[j]
+            send[pos:pos + n].view(rows, self.heads_of[j], d).copy_(t[0][:, self.head_off[j]:self.head_off[j] + self.heads_of[j]])
+            pos += n
+        mine = self.heads_of[sp.rank]
+        recv = self._buf(name + ".r", (sp.total_rows * mine, d), t)
+        work = dist.all_to_all_single(recv, send, output_split_sizes=[r * mine for r in self.rows_of],
+                                      input_split_sizes=[rows * c for c in self.heads_of], group=sp.group, async_op=True)
+        self._pending[name] = (recv.view(sp.total_rows, mine, d), work)
+
+    def __call__(self, q, k, v):
+        sp, w = self.sp, self.sp.world
+        dtype = q.dtype
+        for name, t in (("q", q), ("k", k), ("v", v)):
+            if name not in self._pending:
+                self._to_heads_async(name, t)
+        o = self.prims.attend(self._getter("q"), self._getter("k"), self._getter("v"))       # [1, L, mine, D]
+        o = o[0].contiguous()
+        rows, mine, d = sp.local_rows, o.shape[1], o.shape[2]
+        recv = self._buf("o.r", (rows * self.heads, d), o)
+        dist.all_to_all_single(recv, o.view(sp.total_rows * mine, d), output_split_sizes=[rows * c for c in self.heads_of],
+                               input_split_sizes=[r * mine for r in self.rows_of], group=sp.group)
+        out = torch.empty(1, rows, self.heads, d, dtype=o.dtype, device=o.device)
+        pos = 0
+        for s_ in range(w):                                                 # chunk s = rank s's heads of my rows
+            n = rows * self.heads_of[s_]
+            out[0][:, self.head_off[s_]:self.head_off[s_] + self.heads_of[s_]].copy_(recv[pos:pos + n].view(rows, self.heads_of[s_], d))
+            pos += n
+        return out.to(dtype)
+
+
 class SequenceParallel:
     def __init__(self, total_rows: int, world: Optional[int] = None, rank: Optional[int] = None, group=None):
         self.group = group
@@ -251,18 +310,21 @@ class SequenceParallel:
             # permutes on the critical path); at N=8 Ulysses is (shape B 286.5 vs 346.0 ms/step: 4x fewer bytes and no
             # rank repeats the full-sequence K preparation).  N=4 has not been measured yet and stays on all-gather.
             return "ulysses" if self.world >= 8 and heads % self.world == 0 else "allgather"
-        if mode == "ulysses" and heads % self.world:
-            raise ValueError(f"mode 'ulysses' needs heads % world == 0 (heads={heads}, world={self.world})")
+        if mode == "ulysses" and heads < self.world:
+            raise ValueError(f"mode 'ulysses' needs at least one head per rank (heads={heads}, world={self.world})")
         return mode
 
     def install(self, model, mode: str = "auto") -> str:
         """Replace every block's attention callable by the sequence-parallel one (the reference seam is
         `WanSelfAttention.attn_op.local_attn`, inference/modify_model.py:48-52).  Returns the mode used:
-        "allgather" (K/V all-gather + moment all-reduce, any head count) or "ulysses" (head<->sequence all-to-all)."""
+        "allgather" (K/V all-gather + moment all-reduce, any head count) or "ulysses" (head<->sequence all-to-all; with
+        heads % world != 0 the uneven variant, opt-in only)."""
         used = None
         for blk in model.blocks:
             used = self.pick_mode(blk.heads, mode)
-            if used == "ulysses":
+            if used == "ulysses" and blk.heads % self.world:
+                blk.attn_hook = UnevenUlyssesAttention(self, UlyssesGpuPrims(blk.sla), blk.heads, compute_dtype=blk.sla.dtype)
+            elif used == "ulysses":
                 blk.attn_hook = UlyssesAttention(self, UlyssesGpuPrims(blk.sla), compute_dtype=blk.sla.dtype)
             else:
                 blk.attn_hook = SPAttention(self, GpuPrimitives(blk.sla))
