@@ -71,7 +71,8 @@ def row_quant_int8(x: torch.Tensor, out_q: torch.Tensor = None, out_s: torch.Ten
 
 
 def gemm_int8_post_scale_bias(x_q, x_s, w_q, w_s, bias, out_dtype=torch.bfloat16):
-    """_tl_gemm_int8_post_scale_bias (tilelang_w8a8.py:78-117): C = acc_int32 * sA[i] * sB[j] + bias[j]."""
+    """_tl_gemm_int8_post_scale_bias (tilelang_w8a8.py:78-117): C = acc_int32 * sA[i] * sB[j] + bias[j], evaluated as the
+    reference's compiled kernel does: fma(float(acc) * sA[i], sB[j], bias[j]) (see tools/tilelang_epilogue_probe.py)."""
     require_cuda(x_q, x_s, w_q, w_s, bias)
     m, k = x_q.shape
     n = w_q.shape[0]
