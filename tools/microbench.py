@@ -127,6 +127,49 @@ def main():
         record(full, med, mn, flops=2.0 * m * n * k, bytes_=m * k + n * k + 2 * m * n)
         del a, b
 
+    # the SageSLA pipeline on synthetic q,k,v [1, L, H, D] bf16 (K with a per-channel bias so
+    # smooth-K matters): preparation, block map, linear moments, the fused attention kernel alone, and the whole module.
+    # Attention FLOPs = H * Mblk * topk_blocks * 4*128*64*D (QK^T + PV of the selected blocks).
+    from turbodiffusion_b200.SLA import SageSparseLinearAttention
+    from turbodiffusion_b200.SLA.core import attn_fwd, linear_moments
+    from turbodiffusion_b200.SLA.utils import block_map_from_pools, quant_qk
+    sla_cases = [("A", 32760, 12, 128, (0.1, 0.15, 1.0)), ("A64", 32760, 24, 64, (0.1,)), ("B", 75600, 40, 128, (0.1,)),
+                 ("C", 28672, 32, 128, (0.3,))]
+    for tag, L, H, D, ratios in sla_cases:
+        prefixes = [f"sla_{part}/{tag}/" for part in ("prep", "block_map", "moments", "attn", "module")]
+        if args.filter and not any(args.filter in n or args.filter.startswith(n) for n in prefixes):
+            continue  # (a selected case runs all of its parts: they share the prepared tensors)
+        g = torch.Generator(device="cuda").manual_seed(0)
+        q = torch.randn(1, L, H, D, device=dev, generator=g).bfloat16()
+        k = (torch.randn(1, L, H, D, device=dev, generator=g) + 2 * torch.randn(1, 1, H, D, device=dev, generator=g)).bfloat16()
+        v = torch.randn(1, L, H, D, device=dev, generator=g).bfloat16()
+        mblk, nblk = (L + 127) // 128, (L + 63) // 64
+        if D == 128:
+            med, mn = timeit(lambda: quant_qk(q, k), args.iters)
+            record(f"sla_prep/{tag}/{L}x{H}x{D}", med, mn, bytes_=L * H * D * (2 + 1) + L * H * D * (2 + 2 + 1))
+            prep = quant_qk(q, k)
+            med, mn = timeit(lambda: linear_moments(k, v), args.iters)
+            record(f"sla_moments/{tag}/{L}x{H}x{D}", med, mn, flops=2.0 * L * D * D * H, bytes_=2 * L * H * D * 2)
+            kv, ksum = linear_moments(k, v)
+            kvw = kv.bfloat16().contiguous()
+            pb = torch.zeros(D, device=dev)
+            for r in ratios:
+                topk = min(nblk, int(r * nblk))
+                med, mn = timeit(lambda: block_map_from_pools(prep.q_pool, prep.k_pool, topk), args.iters)
+                record(f"sla_block_map/{tag}/topk{r}", med, mn)
+                _, lut = block_map_from_pools(prep.q_pool, prep.k_pool, topk)
+                med, mn = timeit(lambda: attn_fwd(prep, v, q, lut, topk, kvw, ksum, pb, D ** -0.5), args.iters)
+                record(f"sla_attn/{tag}/topk{r}/{topk}of{nblk}", med, mn, flops=float(H) * mblk * topk * 4 * 128 * 64 * D,
+                       bytes_=4 * L * H * D * 2)
+        for r in ratios:
+            mod = SageSparseLinearAttention(D, r).to(dev)
+            with torch.no_grad():
+                mod.proj_l.weight.normal_(0, 0.05)
+            med, mn = timeit(lambda: mod(q, k, v), max(3, args.iters // 2))
+            topk = min(nblk, int(r * nblk))
+            record(f"sla_module/{tag}/topk{r}", med, mn, flops=float(H) * mblk * topk * 4 * 128 * 64 * D + 6.0 * L * D * D * H)
+        del q, k, v
+
     with open(args.out, "w") as f:
         for r in results:
             f.write(json.dumps(r) + "\n")
