@@ -140,3 +140,52 @@ def test_split_heads_partition(heads, world):
     counts, offs = split_heads(heads, world)
     assert sum(counts) == heads and offs[0] == 0 and max(counts) - min(counts) <= 1
     assert all(offs[i + 1] == offs[i] + counts[i] for i in range(world - 1)) and sorted(counts, reverse=True) == counts
+
+
+def test_proj_l_folding_identity_and_shard_additivity():
+    """Two algebraic facts the fused kernels rely on (SLA/core.py:243-253):
+    (1) proj_l can be folded into the moments:  (phi(q) KV / den) W^T + b == phi(q) (W KV^T)^T / den + b;
+    (2) the moments KV = phi(K)^T V and ksum = sum phi(K) are sums over key rows, so row shards (ranks) simply add."""
+    g = torch.Generator().manual_seed(9)
+    b, h, l, d = 1, 2, 300, 16
+    q, k, v = (torch.randn(b, h, l, d, generator=g).double() for _ in range(3))
+    w, bias = torch.randn(d, d, generator=g).double() * 0.1, torch.randn(d, generator=g).double() * 0.1
+    pq, pk = torch.softmax(q, -1), torch.softmax(k, -1)
+    kv = pk.transpose(-1, -2) @ v                       # [b,h,dk,dv]
+    ks = pk.sum(-2, keepdim=True)
+    den = 1e-5 + (pq * ks).sum(-1, keepdim=True)
+    ref = ((pq @ kv) / den) @ w.t() + bias
+    kvw = w @ kv.transpose(-1, -2)                      # [b,h,d_out,dk]: the K-major B operand the kernel consumes
+    folded = (pq @ kvw.transpose(-1, -2)) / den + bias
+    assert torch.allclose(ref, folded, rtol=1e-12, atol=1e-12)
+    assert torch.allclose(O.linear_branch(q.float(), k.float(), v.float(), w.float(), bias.float(), torch.float32, exact=True).double(),
+                          ref, rtol=1e-4, atol=1e-5)
+    cut = 128                                           # shard boundary (multiple of the 64-row key block)
+    kv2 = pk[..., :cut, :].transpose(-1, -2) @ v[..., :cut, :] + pk[..., cut:, :].transpose(-1, -2) @ v[..., cut:, :]
+    assert torch.allclose(kv, kv2, rtol=1e-12, atol=1e-12)
+    assert torch.allclose(ks, pk[..., :cut, :].sum(-2, keepdim=True) + pk[..., cut:, :].sum(-2, keepdim=True), rtol=1e-12)
+
+
+def test_padded_64_wide_heads_equal_native_64_wide_math():
+    """The d=64 path runs through the 128-wide kernels with zero-padded q/k/v (scores, pooled scores, P.V unchanged) and a
+    large negative pad for the softmax feature map (phi = 0 on padded channels); in exact arithmetic both formulations of
+    the module agree (turbodiffusion_b200/SLA/core.py _forward_d64)."""
+    g = torch.Generator().manual_seed(4)
+    bsz, l, h, d = 1, 200, 2, 64
+    q, k, v = (torch.randn(bsz, l, h, d, generator=g).bfloat16() for _ in range(3))
+    w, bias = torch.randn(d, d, generator=g) * 0.05, torch.randn(d, generator=g) * 0.05
+    ref = O.sla_forward(q, k, v, w, bias, 0.5, mode="exact").float()
+    pad = lambda t, val=0.0: torch.nn.functional.pad(t, (0, 64), value=val)
+    qh, kh, vh = (pad(t).transpose(1, 2).contiguous() for t in (q, k, v))
+    _, lut, _ = O.get_block_map(q.transpose(1, 2).contiguous(), k.transpose(1, 2).contiguous(), 0.5)
+    _, lut_p, _ = O.get_block_map(qh, kh, 0.5)
+    assert torch.equal(lut, lut_p)                                             # zero channels do not move pooled scores
+    o_s = O.sparse_attention(qh, kh, vh, lut, 128, 64, sm_scale=64 ** -0.5)[..., :64]
+    qf, kf = (pad(t, -3.0e4).transpose(1, 2).contiguous() for t in (q, k))
+    w128 = torch.zeros(128, 128)
+    w128[:64, :64] = w
+    b128 = torch.zeros(128)
+    b128[:64] = bias
+    o_l = O.linear_branch(qf, kf, vh, w128, b128, torch.bfloat16, exact=True)[..., :64]
+    got = (o_s + o_l).to(torch.bfloat16).transpose(1, 2).float()
+    assert O.stats(got, ref)["rel_l2"] < 1e-6
