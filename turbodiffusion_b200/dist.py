@@ -107,7 +107,7 @@ class SPAttention:
     def start_kv(self, k, v):
         sp = self.sp
         cdt = self._cdt(k)
-        if getattr(self, "_pending_k", None) is None:
+        if self._pending_k is None:
             self.start_k(k)
         k, k_full, wk = self._pending_k
         self._pending_k = None
