@@ -5,6 +5,7 @@
 # rebuilds only the touched source, runs the parity tests of that kernel, then the microbench lines, and finally restores
 # the default build.  Outputs: gpurun_out/exp_<name>_{build,tests}.log, gpurun_out/exp_<name>_mb.jsonl.
 mkdir -p gpurun_out
+export TDB200_TEST_EXTENDED=1   # include the lazy-rescale attention test (first GPU run pending)
 variant() {  # name  source  defines  pytest-args  microbench-filter
   local name=$1 src=$2 defs=$3 tests=$4 filt=$5
   touch turbodiffusion_b200/csrc/$src

@@ -31,8 +31,8 @@
 #endif
 // -DTDB_ATTN_P_TMEM=1: P(j) is written with tcgen05.st into the first 32 columns of the S buffer it was computed from
 // (S(j) already lives in registers) and P.V reads its A operand from tensor memory (tcgen05.mma [d], [a_tmem], b_desc).
-// That removes the 16 KB st.shared + fence.proxy.async publish and the wait for the single smem P buffer; the in-order
-// tensor pipe keeps Q.K^T(j+2) behind P.V(j), which is what makes the aliasing safe (the MMA warp issues P.V(j) first).
+// That removes the 16 KB st.shared + fence.proxy.async publish; the in-order tensor pipe keeps Q.K^T(j+2) behind P.V(j),
+// which is what makes the aliasing safe (the MMA warp issues P.V(j) first).
 #ifndef TDB_ATTN_P_TMEM
 #define TDB_ATTN_P_TMEM 0
 #endif
@@ -400,7 +400,10 @@ sla_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q8, const __grid_co
       }
 
 #if TDB_ATTN_P_TMEM
-      // ---- P row -> tensor memory: 32 packed columns over the S buffer this block was read from (double-buffered with S)
+      // ---- P row -> tensor memory: 32 packed columns over the S buffer this block was read from.  The wait for P.V(j-1)
+      //      stays: the parity waits on kBarPvDone / kBarPEmpty are only unambiguous while the softmax warps run at most
+      //      one P.V ahead of the tensor pipe (two ahead would alias the phase bit in the lazy-rescale wait above).
+      mbar_wait(&bars[kBarPEmpty], (j & 1) ^ 1);
       TDB_TRACE(tracing, j, 5);
       tmem_st_x32(tmem_base + lane_addr + kColS + uint32_t(st) * BLKK, pw);
       tmem_st_wait();
