@@ -68,3 +68,50 @@ def test_product_does_not_import_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "td_oracle" not in text and "from oracle" not in text and "import oracle" not in text, f
+
+
+def _p(v=4096):
+    return ctypes.c_void_p(v)          # non-null, 16-byte aligned, never dereferenced: validation runs before any CUDA call
+
+
+def test_argument_validation_of_every_kernel_family(libpath):
+    """Every entry point checks pointers / shapes / dtypes first and reports through the return code + tdb200_last_error
+    (never exit(), never a crash), so the contract can be exercised on a machine without a GPU."""
+    from turbodiffusion_b200 import _lib
+    lib = _lib.lib()
+    INVALID, UNSUPPORTED = -1, -2
+    cases = [
+        ("quant null", lambda: lib.tdb200_quant_int8_block128(None, 0, 128, 128, _p(), _p(), None), INVALID, b"null"),
+        ("gemm k%128", lambda: lib.tdb200_gemm_w8a8(_p(), _p(), _p(), _p(), None, _p(), 0, 128, 128, 100, None), UNSUPPORTED, b"128"),
+        ("gemm n%8", lambda: lib.tdb200_gemm_w8a8(_p(), _p(), _p(), _p(), None, _p(), 0, 128, 100, 128, None), UNSUPPORTED, b"multiple of 8"),
+        ("gemm misaligned", lambda: lib.tdb200_gemm_w8a8(_p(4100), _p(), _p(), _p(), None, _p(), 0, 128, 128, 128, None), INVALID, b"aligned"),
+        ("gemm epilogue", lambda: lib.tdb200_gemm_w8a8_ex(_p(), _p(), _p(), _p(), None, _p(), 0, 128, 128, 128, 9, None), INVALID, b"epilogue"),
+        ("rowwise null", lambda: lib.tdb200_gemm_w8a8_rowwise(_p(), _p(), _p(), _p(), None, None, 0, 128, 128, 128, None), INVALID, b"null"),
+        ("rowquant k%8", lambda: lib.tdb200_quant_int8_rowwise(_p(), 0, 4, 12, _p(), _p(), None), INVALID, b"shape"),
+        ("sla prep head dim", lambda: lib.tdb200_sla_quant_qk(_p(), _p(), 0, 1, 256, 256, 2, 96, _p(), _p(), _p(), _p(), _p(), _p(), _p(), None),
+         UNSUPPORTED, b"head dim"),
+        ("block map topk", lambda: lib.tdb200_sla_block_map(_p(), _p(), 0, 1, 2, 4, 8, 128, 9, _p(), _p(), None), INVALID, b"topk"),
+        ("moments head dim", lambda: lib.tdb200_sla_linear_moments(_p(), _p(), 0, 1, 256, 2, 64, _p(), _p(), None), UNSUPPORTED, b"head dim"),
+        ("attn null", lambda: lib.tdb200_sla_attn_fwd(None, _p(), _p(), _p(), _p(), _p(), 0, _p(), 4, _p(), _p(), _p(), _p(), 1, 256, 256, 2,
+                                                      128, 0.088, None), INVALID, b"null"),
+        ("attn topk", lambda: lib.tdb200_sla_attn_fwd(_p(), _p(), _p(), _p(), _p(), _p(), 0, _p(), 9, _p(), _p(), _p(), _p(), 1, 256, 256, 2,
+                                                      128, 0.088, None), INVALID, b"topk"),
+    ]
+    for name, call, code, needle in cases:
+        rc = call()
+        msg = lib.tdb200_last_error() or b""
+        assert rc == code, (name, rc, msg)
+        assert needle in msg, (name, msg)
+
+
+def test_valid_calls_without_a_gpu_report_an_error_code(libpath):
+    """On a CUDA-less host a well-formed call must come back with a negative code and a message (no fallback, no crash)."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("this check is for hosts without a GPU")
+    from turbodiffusion_b200 import _lib
+    lib = _lib.lib()
+    rc = lib.tdb200_gemm_w8a8(_p(), _p(), _p(), _p(), None, _p(), 0, 128, 128, 128, None)
+    assert rc in (-3, -4) and lib.tdb200_last_error()
+    rc = lib.tdb200_quant_int8_block128(_p(), 0, 128, 128, _p(), _p(), None)
+    assert rc in (-3, -4) and lib.tdb200_last_error()
