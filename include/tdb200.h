@@ -211,6 +211,9 @@ int tdb200_debug_set_attn_trace(long long* trace_or_null);
  * tcgen05.ld.32x32b.x64 (8 KB per warp instruction), optionally followed by the GEMM's int->float + FMA dequant.
  * cycles_per_cta [#SMs] receives clock64() deltas. */
 int tdb200_selftest_tmem_read(int warps, int iters, int convert, long long* cycles_per_cta, float* sink, void* stream);
+/* XU (MUFU) throughput probe: mode 0/1/2 = ex2 f32 / bf16x2 / f16x2, 3/4/5 = tanh f32 / bf16x2 / f16x2; one CTA per SM with
+ * `warps` warps, 8 independent chains x `iters` per thread; cycles_per_cta[sm_count]. Diagnostics only. */
+int tdb200_selftest_mufu(int mode, int warps, int iters, long long* cycles_per_cta, float* sink, void* stream);
 
 #ifdef __cplusplus
 }

@@ -421,6 +421,51 @@ def sla_forward(q, k, v, proj_w, proj_b, topk_ratio: float, blkq: int = 128, blk
     return o.to(in_dtype).transpose(1, 2).contiguous()
 
 
+def sla_forward_block(q, k, v, proj_w, proj_b, head: int, m_blk: int, ids: torch.Tensor, blkq: int = 128, blkk: int = 64,
+                      dtype=torch.bfloat16, mode: str = "exact", feature_map: str = "softmax",
+                      batch: int = 0) -> torch.Tensor:
+    """sla_forward restricted to ONE query block of ONE head (full-size parity sampling: the whole tensor would take the
+    CPU minutes).  q,k,v [B,L,H,D]; `ids` = the selected key-block ids of that query block.  Same arithmetic and modes as
+    sla_forward (SLA/core.py:168-257): the key mean, the K quantisation and the linear-attention moments still run over
+    all L keys of the head.  Returns [rows, D] in q.dtype."""
+    in_dtype = q.dtype
+    l, d = q.shape[1], q.shape[3]
+    r0, r1 = m_blk * blkq, min(l, (m_blk + 1) * blkq)
+    qh = q[batch, :, head].to(dtype)[None, None]          # [1,1,L,D]
+    kh = k[batch, :, head].to(dtype)[None, None]
+    vh = v[batch, :, head].to(dtype)[None, None]
+    qb = qh[:, :, r0:r1]
+    lut = ids.reshape(1, 1, 1, -1)
+    if mode == "sage":
+        arg_k, _ = smooth_k(kh)
+        q_i8, q_s = sage_quant_blocks(qb, blkq)
+        k_i8, k_s = sage_quant_blocks(arg_k, blkk)
+        o_s = sparse_attention(qb, kh, vh, lut, blkq, blkk, p_dtype=dtype, q_i8=q_i8, q_s=q_s, k_i8=k_i8, k_s=k_s)
+    elif mode == "triton":
+        o_s = sparse_attention(qb, kh, vh, lut, blkq, blkk, p_dtype=dtype).to(dtype).float()
+    else:
+        o_s = sparse_attention(qb, kh, vh, lut, blkq, blkk)
+    fq, fk = feature_maps(feature_map)
+    pq = fq(qb.float()).to(dtype).float()
+    pk = fk(kh.float()).to(dtype).float()
+    kv = pk.transpose(-1, -2) @ vh.float()
+    ks = pk.sum(-2, keepdim=True)
+    o_l = (pq @ kv) / (1e-5 + (pq * ks).sum(-1, keepdim=True))
+    o_l = o_l @ proj_w.float().t() + proj_b.float()
+    return (o_s + o_l)[0, 0].to(in_dtype)
+
+
+def feature_maps(name: str):
+    """SLA/core.py:57-73: 'softmax' (over D), 'elu' (elu(x)+1), 'relu'."""
+    if name == "softmax":
+        return (lambda x: torch.softmax(x, -1)), (lambda x: torch.softmax(x, -1))
+    if name == "elu":
+        return (lambda x: F.elu(x) + 1), (lambda x: F.elu(x) + 1)
+    if name == "relu":
+        return F.relu, F.relu
+    raise NotImplementedError(f"Not supported feature map {name}.")
+
+
 # =============================================================================================
 # LTX-2 prologue variants (config 5) — ltx_core/model/transformer/transformer.py:21-94, ltx_core/utils.py:7-12
 # =============================================================================================

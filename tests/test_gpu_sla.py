@@ -223,38 +223,61 @@ def test_fp16_block_map_and_quant(cuda):
     assert torch.equal(prep.q_scale.cpu(), q_s) and torch.equal(prep.q_i8.cpu(), q_i8)
 
 
-@pytest.mark.skipif(not os.environ.get("TDB200_TEST_EXTENDED"),
-                    reason="written after round 1's GPU budget was spent; first GPU run pending (set TDB200_TEST_EXTENDED=1)")
-@pytest.mark.parametrize("qscale,l,h,ratio", [(8.0, 1280, 2, 0.5), (16.0, 700, 1, 1.0)])
-def test_sage_sla_forward_large_scores_exercise_the_lazy_rescale(cuda, qscale, l, h, ratio):
-    """With unit-variance q,k the per-block row maxima differ by far less than the lazy-rescale threshold (2^8), so the
-    round-1 cases never take the branch that rescales the O accumulator in tensor memory.  Scaling q makes the log2-domain
-    scores spread over tens of units: the running maximum now grows by more than 8 between key blocks for most rows.
-    Compared against the INT8 emulation (same score quantisation) and, more loosely, the fp32 oracle."""
+@pytest.mark.parametrize("pattern,qscale,l,h,ratio", [
+    ("all", 8.0, 1280, 2, 0.5),          # every row's running maximum jumps by > 2^8 somewhere
+    ("all", 16.0, 700, 1, 1.0),          # dense selection, ragged q tail (60 rows) and k tail (60 keys)
+    ("half_warp", 16.0, 640, 2, 1.0),    # rows 0-15 of every 32-row group are scaled: each warp takes the branch for half its rows
+    ("one_warp", 16.0, 640, 2, 1.0),     # only rows 0-31 of every query block (softmax warp 0) are scaled
+    ("ragged_last", 12.0, 1000, 2, 1.0), # the maximum of many rows sits in the ragged LAST key block (40 valid keys)
+])
+def test_sage_sla_forward_large_scores_exercise_the_lazy_rescale(cuda, pattern, qscale, l, h, ratio):
+    """With unit-variance q,k the per-block row maxima differ by far less than the lazy-rescale threshold (2^8), so ordinary
+    cases never take the branch that rescales the O accumulator in tensor memory.  Scaling q makes the log2-domain scores
+    spread over tens of units: the running maximum grows by more than 8 between key blocks.  Patterns cover a branch taken
+    by all rows, by part of a warp (alpha = 1 for the other rows), by one warp of the CTA only, and a rescale triggered by
+    the ragged last key block.  Compared against the INT8 emulation (same score quantisation) and the fp32 oracle."""
     from turbodiffusion_b200.SLA import SageSparseLinearAttention
     from turbodiffusion_b200.SLA.utils import block_map_from_pools, quant_qk
     d = 128
     q, k, v = _qkv(1, l, h, d, 4000 + l)
-    q = (q.float() * qscale).bfloat16()
+    qf = q.float()
+    rows = torch.arange(l)
+    if pattern == "all" or pattern == "ragged_last":
+        qf = qf * qscale
+    elif pattern == "half_warp":
+        qf[:, (rows % 32) < 16] *= qscale
+    elif pattern == "one_warp":
+        qf[:, (rows % 128) < 32] *= qscale
+    if pattern == "ragged_last":
+        # every query gets a common component along u and the keys of the last (ragged) block point along u, so the row
+        # maximum of most rows sits in that block and exceeds everything seen before by more than 2^8
+        nlast = l - (l // 64) * 64
+        u = torch.ones(d) / d ** 0.5
+        qf = qf + 2.0 * qscale * u
+        kf = k.float()
+        kf[:, -nlast:] += 6.0 * u
+        k = kf.bfloat16()
+    q = qf.bfloat16()
     g = torch.Generator().manual_seed(6)
     mod = SageSparseLinearAttention(d, ratio).to(cuda)
     with torch.no_grad():
         mod.proj_l.weight.copy_(torch.randn(d, d, generator=g) * 0.05)
         mod.proj_l.bias.copy_(torch.randn(d, generator=g) * 0.05)
-    out = mod(q.to(cuda), k.to(cuda), v.to(cuda))
+    out, sel = mod.forward_with_lut(q.to(cuda), k.to(cuda), v.to(cuda))
     torch.cuda.synchronize()
     assert not torch.isnan(out.float()).any() and not torch.isinf(out.float()).any()
-    prep = quant_qk(q.to(cuda), k.to(cuda))
-    topk = min(prep.nblk, int(ratio * prep.nblk))
-    _, lut = block_map_from_pools(prep.q_pool, prep.k_pool, topk)
-    lut = lut.cpu()
+    lut = sel["lut"].cpu()
     w, bias = mod.proj_l.weight.detach().cpu(), mod.proj_l.bias.detach().cpu()
     # how often the branch is taken according to the oracle's scores: rows whose running max grows by > 8 (log2 units)
     qh, kh = q.transpose(1, 2).float(), k.transpose(1, 2).float()
     s = (qh @ (kh - kh.mean(-2, keepdim=True)).transpose(-1, -2)) * (d ** -0.5) * 1.4426950408889634
     blk_max = torch.stack([s[..., i:i + 64].amax(-1) for i in range(0, l, 64)], -1)        # [1,h,l,nblk] (dense order)
     run_max = torch.cummax(blk_max, -1).values
-    assert ((run_max[..., 1:] - run_max[..., :-1]) > 8).any(-1).float().mean() > 0.3
+    grows = (run_max[..., 1:] - run_max[..., :-1]) > 8
+    frac = grows.any(-1).float().mean().item()
+    assert frac > (0.3 if pattern in ("all", "ragged_last") else 0.08), frac
+    if pattern == "ragged_last":
+        assert grows[..., -1].float().mean() > 0.2, "the ragged last block should trigger the rescale for many rows"
     sage = O.sla_forward(q, k, v, w, bias, ratio, mode="sage", lut=lut)
     exact = O.sla_forward(q, k, v, w, bias, ratio, mode="exact", lut=lut)
     s_sage, s_exact = O.stats(out.cpu(), sage), O.stats(out.cpu(), exact)

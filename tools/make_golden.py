@@ -115,6 +115,29 @@ for tag, (bsz, h, l, d, topk) in ({"sla_a": (1, 2, 600, 128, 0.25), "sla_b": (2,
          topk=real_topk, topk_ratio=topk, proj_w=mod.proj_l.weight.detach().clone(),
          proj_b=mod.proj_l.bias.detach().clone(), o_s=o_s, out=out)
 
+# ---- full-size block maps (Nblk = 512 for Wan-1.3B 480p, 1182 for Wan-14B 720p): the reference's own get_block_map on seeded
+#      inputs.  q,k are NOT stored (tens of MB): the test regenerates them on the CPU from the same generator and checks
+#      their checksum; the fixture holds the pooled means, the bf16 scores and the selected map (a few MB).
+def blockmap_inputs(l, h, d, seed):
+    """Shared with tests/test_gpu_blockmap_golden.py (must stay byte-identical there)."""
+    g = torch.Generator().manual_seed(seed)
+    q = torch.randn(1, h, l, d, generator=g).bfloat16()
+    k = (torch.randn(1, h, l, d, generator=g) + torch.randn(1, h, 1, d, generator=g) * 2.0).bfloat16()
+    return q, k
+
+
+for tag, (l, h, d, topk, seed) in ({"blockmap_n512": (32760, 2, 128, 0.1, 512), "blockmap_n1182": (75600, 2, 128, 0.1, 1182),
+                                    "blockmap_n512_d64": (32760, 2, 64, 0.15, 564)}.items() if want("blockmap") else ()):
+    qh, kh = blockmap_inputs(l, h, d, seed)
+    pooled_q = ref_utils.mean_pool(qh, 128)
+    arg_k = kh - torch.mean(kh, dim=-2, keepdim=True)
+    pooled_k = ref_utils.mean_pool(arg_k, 64)
+    score = pooled_q @ pooled_k.transpose(-1, -2)
+    sparse_map, lut, real_topk = ref_utils.get_block_map(qh, kh, topk_ratio=topk, BLKQ=128, BLKK=64)
+    csum = torch.stack([qh.view(torch.int16).to(torch.int64).sum(), kh.view(torch.int16).to(torch.int64).sum()])
+    save(tag, l=l, h=h, d=d, seed=seed, checksum=csum, kmean=torch.mean(kh, dim=-2), pooled_q=pooled_q, pooled_k=pooled_k,
+         score=score, sparse_map=sparse_map, topk=real_topk, topk_ratio=topk)
+
 # ---- LTX per-row INT8 quantisation (TurboT2AV ltx_distillation/tilelang_w8a8.py:16-36), the Triton kernel itself
 if want("ltx"):
     import importlib.util

@@ -84,6 +84,13 @@ def main():
             c = torch.empty(m, n, dtype=torch.bfloat16, device=dev)
             med, mn = timeit(lambda: tdo.gemm_cuda(a, a_s, b, b_s, c), args.iters)
             record(full, med, mn, flops=2.0 * m * n * k, bytes_=m * k + n * k + 2 * m * n)
+            bias = torch.randn(n, device=dev).bfloat16()
+            if name in ("o_proj", "ffn_down"):   # the epilogues the block actually runs: +bias; +bias+GELU+int8 block quant
+                med, mn = timeit(lambda: tdo.gemm_cuda_swizzle_bias(a, a_s, b, b_s, c, bias), args.iters)
+                record(full.replace("gemm_w8a8/", "gemm_w8a8_bias/"), med, mn, flops=2.0 * m * n * k, bytes_=m * k + n * k + 2 * m * n)
+            if name == "ffn_up":
+                med, mn = timeit(lambda: tdo.gemm_cuda_quant_out(a, a_s, b, b_s, bias, torch.bfloat16, gelu=True), args.iters)
+                record(full.replace("gemm_w8a8/", "gemm_w8a8_gelu_quant/"), med, mn, flops=2.0 * m * n * k, bytes_=m * k + n * k + m * n)
             del a, b, c
         for name, k in (("dim", dim), ("ffn", ffn)):
             full = f"quant_int8/{tag}/{name}/{L}x{k}"

@@ -72,6 +72,17 @@ class _SLABase(nn.Module):
         o = o.to(dtype)
         return (o, ratio) if return_sparsity else o
 
+    def forward_with_lut(self, q, k, v):
+        """forward() that also returns the block selection it used: (o, {"lut": int32 [B,H,Mblk,topk] ascending key-block
+        ids, "sparse_map": int8 [B,H,Mblk,Nblk], "topk": int}).  Test/diagnostic entry point (sampled oracle parity at
+        full shapes needs the kernel's own selection)."""
+        self._keep_selection = {}
+        try:
+            o = self.forward(q, k, v)
+            return o, self._keep_selection
+        finally:
+            self._keep_selection = None
+
     def _forward_d128(self, q, k, v, q_feat, k_feat, sm_scale, proj_w, proj_b):
         """q,k,v: tensors the sparse branch sees; q_feat,k_feat: tensors the softmax feature map sees (they differ only for
         padded 64-wide heads)."""
@@ -79,6 +90,8 @@ class _SLABase(nn.Module):
         nblk = prep.nblk
         real_topk = min(nblk, int(self.topk * nblk))
         sparse_map, lut = block_map_from_pools(prep.q_pool, prep.k_pool, real_topk)
+        if getattr(self, "_keep_selection", None) is not None:
+            self._keep_selection.update(lut=lut, sparse_map=sparse_map, topk=real_topk)
         kv, ksum = linear_moments(k_feat, v)
         # proj_l folded into the moments: (phi(q) KV / den) W^T + b == phi(q) (W KV^T)^T / den + b ; kv is [dv, dk]
         kvw = torch.matmul(proj_w.float(), kv).to(self.dtype).contiguous()  # [B,H,d_out,d_k]

@@ -50,6 +50,7 @@ _PROTOS = {
     "tdb200_debug_set_attn_trace": [_P],
     "tdb200_selftest_umma_bf16": [_P, _P, _P, _P],
     "tdb200_selftest_tmem_read": [_I, _I, _I, _P, _P, _P],
+    "tdb200_selftest_mufu": [_I, _I, _I, _P, _P, _P],
 }
 _RESTYPES = {"tdb200_last_error": c_char_p}
 
@@ -79,8 +80,37 @@ def lib() -> ctypes.CDLL:
             fn.restype = _RESTYPES.get(name, c_int)
         if handle.tdb200_abi_version() != 1:
             raise Tdb200Error("libtdb200.so ABI version mismatch")
-        _lib = handle
+        _lib = _DeviceGuarded(handle)
     return _lib
+
+
+_CALL_DEVICE = None  # device index of the tensors of the call being assembled (set by stream_ptr)
+
+
+class _DeviceGuarded:
+    """The C side works on the CUDA runtime's *current* device (cudaGetDevice) with the stream handed in.  Every Python
+    wrapper evaluates stream_ptr(tensor.device) while building its argument list; if that device is not the current one,
+    the call is made under torch.cuda.device(...) so tensors on a non-current GPU work like they do for torch ops."""
+
+    def __init__(self, handle):
+        self._handle = handle
+        self._cache = {}
+
+    def __getattr__(self, name):
+        fn = self._cache.get(name)
+        if fn is None:
+            raw = getattr(self._handle, name)
+
+            def fn(*args, _raw=raw):
+                global _CALL_DEVICE
+                dev, _CALL_DEVICE = _CALL_DEVICE, None
+                if dev is not None and dev != torch.cuda.current_device():
+                    with torch.cuda.device(dev):
+                        return _raw(*args)
+                return _raw(*args)
+
+            self._cache[name] = fn
+        return fn
 
 
 LAUNCHES = 0  # kernels launched through the C ABI (each entry point documents how many it enqueues)
@@ -96,6 +126,10 @@ def check(rc: int, what: str, launches: int = None) -> None:
 
 
 def stream_ptr(device=None) -> int:
+    global _CALL_DEVICE
+    if device is not None:
+        dev = torch.device(device)
+        _CALL_DEVICE = dev.index if dev.index is not None else torch.cuda.current_device()
     return torch.cuda.current_stream(device).cuda_stream
 
 

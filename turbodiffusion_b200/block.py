@@ -54,6 +54,13 @@ class WanBlockB200:
     """One DiT block on the B200 operators.  `sd` uses the reference state-dict keys relative to `blocks.<i>.`."""
 
     def __init__(self, sd: Dict[str, torch.Tensor], dim: int, heads: int, eps: float = 1e-6, topk: float = 0.1):
+        # norm weights / modulation are read by the fused kernels through fp32 pointers: a checkpoint loaded with
+        # load_state_dict(assign=True) may hold them in bf16, so normalise them ONCE here (no per-call casts)
+        sd = dict(sd)
+        for key in ("self_attn.norm_q.weight", "self_attn.norm_k.weight", "cross_attn.norm_q.weight", "cross_attn.norm_k.weight",
+                    "norm3.weight", "norm3.bias", "modulation"):
+            if key in sd and (sd[key].dtype != torch.float32 or not sd[key].is_contiguous()):
+                sd[key] = sd[key].float().contiguous()
         self.sd, self.dim, self.heads, self.eps = sd, dim, heads, eps
         self.head_dim = dim // heads
         dev = sd["modulation"].device

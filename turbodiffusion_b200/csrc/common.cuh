@@ -111,6 +111,27 @@ __device__ __forceinline__ void tma_load_2d_mcast(void* smem_dst, const void* tm
       : "memory");
 }
 
+// TMA store: one thread hands a swizzled smem box to the copy engine; out-of-range rows/columns are clipped by the map.
+__device__ __forceinline__ void tma_store_2d(const void* tmap, const void* smem_src, int32_t c0, int32_t c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(tmap)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const void* tmap, const void* smem_src, int32_t c0, int32_t c1, int32_t c2,
+                                             int32_t c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(tmap)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all but the newest kKeep store groups of this thread have finished READING shared memory (the buffers may be reused)
+template <int kKeep>
+__device__ __forceinline__ void tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kKeep) : "memory");
+}
+
 // ------------------------------------------------------------------------------------------
 // thread-block clusters
 // ------------------------------------------------------------------------------------------

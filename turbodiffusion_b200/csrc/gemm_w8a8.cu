@@ -5,39 +5,33 @@
 //
 // Design (one persistent CTA per SM, 128x256 output tile, 128-deep K-blocks):
 //   warp 8   TMA producer: A tile [128 rows x 128 B] and B tile [256 rows x 128 B] per K-block, 128B-swizzled,
-//            4-stage ring, mbarrier complete_tx.
+//            3-stage ring, mbarrier complete_tx.
 //   warp 9   MMA issuer (one elected lane): 4 x tcgen05.mma.kind::i8 (M128 N256 K32) per K-block into one of two
 //            TMEM accumulator buffers (2 x 256 columns of int32), accumulate flag reset at every K-block because the
 //            reference rescales per K-block; tcgen05.commit releases the smem stage and publishes the TMEM buffer.
-//   warps 0-7 dequant/epilogue: thread = one output row (TMEM lane) x 128 columns.  Per K-block: tcgen05.ld the
-//            int32 partial sums, cvt to fp32 (exact, |sum| < 2^22) and FMA with the block scale into 128 fp32
-//            registers, hand the TMEM buffer back; after the last K-block: round to T, add bias, 16-byte stores.
-//            The dequant of K-block kb overlaps the MMAs of K-block kb+1 (double-buffered TMEM).
-// Measured alternatives (profiles/r01_gemm_experiments.md): 16 dequant warps x 64 columns is ~8% SLOWER; TMA multicast of
-// the B tile inside 2-CTA clusters (kept: -33% L2->SM traffic) is throughput-neutral; a tcgen05.ld probe shows the
-// dequant loop alone runs at 782 clk per K-block (ALU floor 512, I2FP issues on the half-rate ALU pipe), the kernel at
-// ~1100: the remainder is hand-off latency and TMEM port sharing with the MMA's accumulator read-modify-writes.
+//   warps 0-7 dequant/epilogue: thread = one output row (TMEM lane) x 128 columns.  Per K-block: four tcgen05.ld.x32
+//            chunks, software-pipelined (chunk c+1 is in flight while chunk c is converted, and chunk 0 of K-block
+//            kb+1 is requested before the last chunk of kb is converted), I2FP (exact, |sum| <= 2^21) + packed FFMA2
+//            with the block scale into 128 fp32 registers; the TMEM buffer is handed back as soon as its last chunk
+//            has landed in registers.  After the last K-block: round to T, (+bias), (GELU), write the warp's 32 x 128
+//            slice into its own swizzled staging buffer and hand it to the TMA store engine
+//            (cp.async.bulk.tensor store, clipped at the M/N edges by the tensor map); the warp moves on to the next
+//            tile while the store drains.
+// Measured (profiles/r01_gemm_experiments.md, profiles/r02_gemm_experiments.md): the chunk pipelining is +20..27 % over
+// load-wait-convert; 16 dequant warps x 64 columns is ~8 % slower; TMA multicast of the B tile inside 2-CTA clusters
+// (kept: -33 % L2->SM traffic) is throughput-neutral; converting a share of the partial sums on the XU pipe (I2F.RM)
+// is slower.  I2FP issues on the half-rate ALU pipe: 512 clk per 128x256 K-block, the same as its int8 MMA.
 // Integer accumulation is exact and the fp32 FMA chain runs in ascending kb order, so the result is bit-identical
 // to the reference restatement (oracle.int8_linear) on the same int8 inputs.
 #include "common.cuh"
 #include "host_common.h"
-
-// Build-time experiment switch (default 0 = the measured round-1 kernel).  Enable with
-//   TDB200_NVCC_DEFINES="-DTDB_GEMM_CVT_MIX=1" python -m turbodiffusion_b200._build --force
-// Results are bit-identical by construction (exact conversions, IEEE fma); only the pipe mix of the dequant loop changes.
-#ifndef TDB_GEMM_CVT_MIX
-#define TDB_GEMM_CVT_MIX 0
-#endif
-#ifndef TDB_GEMM_LD_PIPE
-#define TDB_GEMM_LD_PIPE 0
-#endif
 
 namespace {
 
 using namespace tdb;
 
 constexpr int BM = 128, BN = 256, BK = 128;
-constexpr int kStages = 4;
+constexpr int kStages = 3;
 constexpr int kEpiWarps = 8;
 constexpr int kTmaWarp = 8, kMmaWarp = 9;
 constexpr int kThreads = 384;  // warps 0-7 dequant/epilogue, 8 TMA, 9 MMA, 10-11 idle (complete the warpgroup)
@@ -45,8 +39,10 @@ constexpr uint32_t kATile = BM * BK;            // 16 KB
 constexpr uint32_t kBTile = BN * BK;            // 32 KB
 constexpr uint32_t kStageBytes = kATile + kBTile;
 constexpr uint32_t kTmemCols = 512;             // 2 accumulator buffers x 256 int32 columns
-constexpr uint32_t kCStageBytes = 32 * 128;     // per-warp output staging: 32 rows x 64 columns of T (swizzled)
-constexpr size_t kSmemBytes = 1024 /*align slack*/ + size_t(kStages) * kStageBytes + kEpiWarps * kCStageBytes + 256 /*barriers*/;
+constexpr uint32_t kCStageBytes = 2 * 32 * 128;  // per-warp output staging: 32 rows x 128 columns of T = two swizzled 4 KB boxes
+constexpr uint32_t kBiasSlot = 256;              // per-warp copy of the tile's 128 bias values (T)
+constexpr size_t kSmemBytes = 1024 /*align slack*/ + size_t(kStages) * kStageBytes + kEpiWarps * (kCStageBytes + kBiasSlot) +
+                              256 /*barriers*/;
 
 struct GemmParams {
   const float* a_s;
@@ -69,11 +65,13 @@ struct GemmParams {
 // c = T(float(acc) * a_s[i] * b_s[j] + bias[j]).  No per-K-block dequant, so the tensor pipe is the limiter.
 template <typename T, bool kCluster, bool kRowScale>
 __global__ void __launch_bounds__(kThreads, 1)
-gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, GemmParams p) {
+gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                 const __grid_constant__ CUtensorMap tmap_c, GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // 1024-aligned, stays a shared-space pointer
-  uint8_t* c_stage = smem + size_t(kStages) * kStageBytes;  // [kEpiWarps][32 rows][128 B]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(c_stage + kEpiWarps * kCStageBytes);
+  uint8_t* c_stage = smem + size_t(kStages) * kStageBytes;  // [kEpiWarps][2 boxes][32 rows][128 B]
+  uint8_t* bias_slots = c_stage + kEpiWarps * kCStageBytes;  // [kEpiWarps][128 x T]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bias_slots + kEpiWarps * kBiasSlot);
   uint64_t* full_bar = bars;                      // [kStages]  TMA -> MMA
   uint64_t* empty_bar = bars + kStages;           // [kStages]  MMA -> TMA
   uint64_t* tmem_full = bars + 2 * kStages;       // [2]        MMA -> epilogue
@@ -107,6 +105,7 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   if (warp == kTmaWarp && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
+    tma_prefetch_desc(&tmap_c);
   }
   tc_fence_before_sync();
   if (kCluster) cluster_sync_all(); else __syncthreads();  // barrier inits visible cluster-wide before any remote arrive
@@ -241,6 +240,11 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       }
       const float* as_row = p.a_s + int64_t(m_tile < p.m_tiles ? m_tile : p.m_tiles - 1) * p.k_blocks;  // odd tail pair
       const float* bs_row = p.b_s + (half_active ? (col0 >> 7) : 0) * p.k_blocks;
+      const T* bias = static_cast<const T*>(p.bias);
+      // this warp's 128 bias values: lanes 0-15 fetch 16 bytes each now, the values go to shared memory at the epilogue
+      uint4 bias_reg = make_uint4(0u, 0u, 0u, 0u);
+      if (bias != nullptr && half_active && lane < 16 && col0 + lane * 8 < p.n)
+        bias_reg = __ldg(reinterpret_cast<const uint4*>(bias + col0) + lane);
 
       float acc[128];
 #pragma unroll
@@ -249,80 +253,58 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       // block scales are fetched one K-block ahead and only multiplied when used, so the global-load latency hides
       // behind the previous K-block's dequant instead of stalling in front of the barrier wait
       float as_next = __ldg(as_row), bs_next = __ldg(bs_row);
-      for (int kb = 0; kb < p.k_blocks; ++kb, ++it) {
+      uint32_t ra[32], rb[32];
+      auto dq32 = [&](uint32_t (&r)[32], int base, float scale) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          const float f0 = __int2float_rn(static_cast<int>(r[j]));
+          const float f1 = __int2float_rn(static_cast<int>(r[j + 1]));
+          const float2 a = __ffma2_rn(make_float2(f0, f1), make_float2(scale, scale), make_float2(acc[base + j], acc[base + j + 1]));
+          acc[base + j] = a.x;
+          acc[base + j + 1] = a.y;
+        }
+      };
+      {  // first chunk of the tile's first K-block
         const uint32_t buf = it & 1u, bphase = (it >> 1) & 1u;
+        mbar_wait(&tmem_full[buf], bphase);
+        tc_fence_after_sync();
+        tmem_ld_x32(tmem_base + lane_addr + buf * BN + half * 128, ra);
+      }
+      for (int kb = 0; kb < p.k_blocks; ++kb, ++it) {
+        const uint32_t buf = it & 1u;
         const float scale = as_next * bs_next;
         if (kb + 1 < p.k_blocks) {
           as_next = __ldg(as_row + kb + 1);
           bs_next = __ldg(bs_row + kb + 1);
         }
-        mbar_wait(&tmem_full[buf], bphase);
-        tc_fence_after_sync();
         const uint32_t t0 = tmem_base + lane_addr + buf * BN + half * 128;
-#if TDB_GEMM_LD_PIPE
-        // Experiment (off by default): four 32-column chunks, the load of chunk c+1 is issued before chunk c is converted,
-        // so the TMEM read latency overlaps the I2FP/FFMA work of the same warp (128 + 2*32 live registers instead of 128 + 64).
-        {
-          uint32_t ra[32], rb[32];
-          auto dq32 = [&](uint32_t (&r)[32], int base) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 2) {
-              const bool xu = TDB_GEMM_CVT_MIX && ((j >> 1) % 5) == 4;  // see the CVT_MIX note below
-              const float f0 = xu ? __int2float_rd(static_cast<int>(r[j])) : __int2float_rn(static_cast<int>(r[j]));
-              const float f1 = xu ? __int2float_rd(static_cast<int>(r[j + 1])) : __int2float_rn(static_cast<int>(r[j + 1]));
-              const float2 a = __ffma2_rn(make_float2(f0, f1), make_float2(scale, scale), make_float2(acc[base + j], acc[base + j + 1]));
-              acc[base + j] = a.x;
-              acc[base + j + 1] = a.y;
-            }
-          };
-          tmem_ld_x32(t0, ra);
-          tmem_ld_wait();
-          tmem_ld_x32(t0 + 32, rb);
-          reg_fence_x32(ra);
-          dq32(ra, 0);
-          tmem_ld_wait();
-          tmem_ld_x32(t0 + 64, ra);
-          reg_fence_x32(rb);
-          dq32(rb, 32);
-          tmem_ld_wait();
-          tmem_ld_x32(t0 + 96, rb);
-          reg_fence_x32(ra);
-          dq32(ra, 64);
-          tmem_ld_wait();
-          reg_fence_x32(rb);
-          dq32(rb, 96);
-        }
-#else
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          uint32_t r[64];
-          tmem_ld_x64(t0 + c * 64, r);
-          tmem_ld_wait();
-#if TDB_GEMM_CVT_MIX
-          // Experiment (off by default, see the note at the top of this file): the int32 partial sums are < 2^24 in
-          // magnitude, so every rounding mode converts them exactly; __int2float_rd compiles to I2F.RM on the otherwise
-          // idle XU pipe while __int2float_rn is I2FP on the ALU pipe.  One pair in five goes to the XU (quarter rate vs
-          // half rate balances at 4:1) and the accumulate is the packed FFMA2 (same IEEE fma per lane).
-#pragma unroll
-          for (int j = 0; j < 64; j += 2) {
-            const bool xu = ((j >> 1) % 5) == 4;
-            const float f0 = xu ? __int2float_rd(static_cast<int>(r[j])) : __int2float_rn(static_cast<int>(r[j]));
-            const float f1 = xu ? __int2float_rd(static_cast<int>(r[j + 1])) : __int2float_rn(static_cast<int>(r[j + 1]));
-            const float2 a = __ffma2_rn(make_float2(f0, f1), make_float2(scale, scale),
-                                        make_float2(acc[c * 64 + j], acc[c * 64 + j + 1]));
-            acc[c * 64 + j] = a.x;
-            acc[c * 64 + j + 1] = a.y;
-          }
-#else
-#pragma unroll
-          for (int j = 0; j < 64; ++j)
-            acc[c * 64 + j] = fmaf(__int2float_rn(static_cast<int>(r[j])), scale, acc[c * 64 + j]);
-#endif
-        }
-#endif  // TDB_GEMM_LD_PIPE
+        // chunk c+1 is in flight while chunk c is converted (ra/rb alternate); tcgen05.wait::ld covers the one load
+        // that is outstanding at that point
+        tmem_ld_wait();
+        tmem_ld_x32(t0 + 32, rb);
+        reg_fence_x32(ra);
+        dq32(ra, 0, scale);
+        tmem_ld_wait();
+        tmem_ld_x32(t0 + 64, ra);
+        reg_fence_x32(rb);
+        dq32(rb, 32, scale);
+        tmem_ld_wait();
+        tmem_ld_x32(t0 + 96, rb);
+        reg_fence_x32(ra);
+        dq32(ra, 64, scale);
+        tmem_ld_wait();
+        // every column of this buffer is in registers: hand it back to the MMA warp before converting the last chunk
         tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+        if (kb + 1 < p.k_blocks) {  // request chunk 0 of the next K-block (its MMAs normally finished long ago)
+          const uint32_t nbuf = (it + 1) & 1u, nphase = ((it + 1) >> 1) & 1u;
+          mbar_wait(&tmem_full[nbuf], nphase);
+          tc_fence_after_sync();
+          tmem_ld_x32(tmem_base + lane_addr + nbuf * BN + half * 128, ra);
+        }
+        reg_fence_x32(rb);
+        dq32(rb, 96, scale);
       }
 
       // ---- optional activation: nn.GELU(approximate="tanh") evaluated in fp32 on the T-rounded pre-activation
@@ -334,12 +316,16 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(inner));
         return 0.5f * x * (1.0f + t);
       };
-      // ---- tile epilogue: round to T, (+bias), (GELU), then write through a per-warp swizzled smem buffer so that
-      //      every global store instruction covers four complete 128-byte lines (a thread owns one ROW of the tile,
-      //      so storing straight from registers would touch 32 different rows per instruction).
+      // ---- tile epilogue.  The warp owns rows [row0, row0+32) x columns [col0, col0+128) of the tile; a thread owns one
+      //      ROW, so the values go through the warp's private swizzled staging buffer and leave as TMA box stores (the
+      //      tensor map clips rows >= m and columns >= n).  The buffer is reused one tile later: by then the store
+      //      engine has read it (wait_group.read), and the warp never waits for the global write itself.
       const int64_t row0 = int64_t(m_tile) * BM + q4 * 32;
-      const T* bias = static_cast<const T*>(p.bias);
       uint8_t* stage = c_stage + warp * kCStageBytes;
+      uint8_t* bslot = bias_slots + warp * kBiasSlot;
+      if (lane == 0) tma_store_wait_read<0>();   // previous tile's boxes have left the staging buffer
+      if (lane < 16) *reinterpret_cast<uint4*>(bslot + lane * 16) = bias_reg;
+      __syncwarp();
       if (p.out_q != nullptr) {
         // ---- fused a1: this thread's 128 values are one row of the 128x128 quant block (m_tile, col0/128).
         //      y = the T-rounded value the plain epilogue would store; amax over the block; q = sat_s8(rint(y*128/amax)).
@@ -347,11 +333,8 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         float amax = 1e-8f;
 #pragma unroll
         for (int ch = 0; ch < 16; ++ch) {
-          uint32_t bw[4] = {0u, 0u, 0u, 0u};
-          if (bias != nullptr && half_active) {
-            const uint4 b4 = *reinterpret_cast<const uint4*>(bias + col0 + ch * 8);
-            bw[0] = b4.x; bw[1] = b4.y; bw[2] = b4.z; bw[3] = b4.w;
-          }
+          const uint4 b4 = *reinterpret_cast<const uint4*>(bslot + ch * 16);
+          const uint32_t bw[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             float y = acc[ch * 8 + j];
@@ -386,58 +369,48 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           }
           *reinterpret_cast<uint4*>(stage + lane * 128 + ((ch ^ (lane & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
         }
+        fence_proxy_async_smem();
         __syncwarp();
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int rr = 4 * i + (lane >> 3), cc = lane & 7;
-          const uint4 v = *reinterpret_cast<const uint4*>(stage + rr * 128 + ((cc ^ (rr & 7)) << 4));
-          const int64_t grow = row0 + rr;
-          if (half_active && grow < p.m) stg_v4(p.out_q + grow * p.n + col0 + cc * 16, v);
+        if (lane == 0 && half_active) {
+          tma_store_2d(&tmap_c, stage, int32_t(col0), int32_t(row0));  // int8 box: 128 columns x 32 rows
+          tma_store_commit();
         }
-        __syncwarp();
         named_bar_sync(1 + half, 128);  // amax_x is reused by the next tile
         continue;
       }
 #pragma unroll
-      for (int pass = 0; pass < 2; ++pass) {  // 64 columns per pass
-        const int64_t colp = col0 + pass * 64;
-#pragma unroll
-        for (int ch = 0; ch < 8; ++ch) {
-          uint32_t w[4];
-          uint32_t bw[4] = {0u, 0u, 0u, 0u};
-          const bool chunk_in = half_active && colp + ch * 8 < p.n;  // n % 8 == 0: a chunk is fully in or out
-          if (bias != nullptr && chunk_in) {
-            const uint4 b4 = *reinterpret_cast<const uint4*>(bias + colp + ch * 8);
-            bw[0] = b4.x; bw[1] = b4.y; bw[2] = b4.z; bw[3] = b4.w;
-          }
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            float y0 = acc[pass * 64 + ch * 8 + 2 * j], y1 = acc[pass * 64 + ch * 8 + 2 * j + 1];
-            if (bias != nullptr) {
-              y0 = F16Traits<T>::round(y0) + F16Traits<T>::lo(bw[j]);
-              y1 = F16Traits<T>::round(y1) + F16Traits<T>::hi(bw[j]);
-            }
-            if (act_gelu) {
-              y0 = gelu(F16Traits<T>::round(y0));
-              y1 = gelu(F16Traits<T>::round(y1));
-            }
-            w[j] = F16Traits<T>::pack(y0, y1);
-          }
-          *reinterpret_cast<uint4*>(stage + lane * 128 + ((ch ^ (lane & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+      for (int ch = 0; ch < 16; ++ch) {  // 8 columns per 16-byte chunk; box 0 = columns 0-63, box 1 = columns 64-127
+        uint32_t w[4];
+        uint32_t bw[4] = {0u, 0u, 0u, 0u};
+        if (bias != nullptr) {
+          const uint4 b4 = *reinterpret_cast<const uint4*>(bslot + ch * 16);
+          bw[0] = b4.x; bw[1] = b4.y; bw[2] = b4.z; bw[3] = b4.w;
         }
-        __syncwarp();
-        // read back: instruction i moves rows 4i..4i+3; 8 lanes cover one row's 128 contiguous bytes
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int rr = 4 * i + (lane >> 3), cc = lane & 7;
-          const uint4 v = *reinterpret_cast<const uint4*>(stage + rr * 128 + ((cc ^ (rr & 7)) << 4));
-          const int64_t grow = row0 + rr;
-          if (half_active && grow < p.m && colp + cc * 8 < p.n)
-            stg_v4(static_cast<T*>(p.c) + grow * p.n + colp + cc * 8, v);
+        for (int j = 0; j < 4; ++j) {
+          float y0 = acc[ch * 8 + 2 * j], y1 = acc[ch * 8 + 2 * j + 1];
+          if (bias != nullptr) {
+            y0 = F16Traits<T>::round(y0) + F16Traits<T>::lo(bw[j]);
+            y1 = F16Traits<T>::round(y1) + F16Traits<T>::hi(bw[j]);
+          }
+          if (act_gelu) {
+            y0 = gelu(F16Traits<T>::round(y0));
+            y1 = gelu(F16Traits<T>::round(y1));
+          }
+          w[j] = F16Traits<T>::pack(y0, y1);
         }
-        __syncwarp();
+        *reinterpret_cast<uint4*>(stage + (ch >> 3) * 4096 + lane * 128 + (((ch & 7) ^ (lane & 7)) << 4)) =
+            make_uint4(w[0], w[1], w[2], w[3]);
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0 && half_active) {
+        tma_store_2d(&tmap_c, stage, int32_t(col0), int32_t(row0));
+        if (col0 + 64 < p.n) tma_store_2d(&tmap_c, stage + 4096, int32_t(col0 + 64), int32_t(row0));
+        tma_store_commit();
       }
     }
+    if (lane == 0) tma_store_wait_read<0>();  // shared memory must outlive the last store's reads
   }
 
   tc_fence_before_sync();
@@ -449,11 +422,17 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 }
 
 template <typename T, bool kCluster, bool kRowScale>
-int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmParams& p, cudaStream_t st) {
   auto kern = gemm_w8a8_kernel<T, kCluster, kRowScale>;
-  if (int rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemBytes)),
-                          "cudaFuncSetAttribute(gemm_w8a8)"))
-    return rc;
+  static bool attr_set[64] = {false};  // per device: the attribute is sticky, no need to set it on every launch
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+    if (int rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemBytes)),
+                            "cudaFuncSetAttribute(gemm_w8a8)"))
+      return rc;
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
+  }
   int grid = kCluster ? 2 * p.total_tiles : p.total_tiles;
   const int cap = kCluster ? (sm_count() & ~1) : sm_count();
   if (grid > cap) grid = cap;
@@ -469,7 +448,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cu
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return check_cuda(cudaLaunchKernelEx(&cfg, kern, ta, tb, p), "gemm_w8a8_kernel launch");
+  return check_cuda(cudaLaunchKernelEx(&cfg, kern, ta, tb, tc, p), "gemm_w8a8_kernel launch");
 }
 
 }  // namespace
@@ -527,12 +506,22 @@ static int gemm_impl(const int8_t* a_q, const float* a_s, const int8_t* b_q, con
 
   const int64_t m_tiles = cdiv64(m, BM);
   const bool use_cluster = m_tiles >= 2;  // pairs of vertically adjacent tiles share the B tile by TMA multicast
-  CUtensorMap ta, tb;
+  if (c_dtype != TDB200_DTYPE_BF16 && c_dtype != TDB200_DTYPE_FP16)
+    return fail(TDB200_ERR_UNSUPPORTED, "gemm_w8a8: output dtype tag %d (bf16/fp16 only, gemm.cu:41-65)", c_dtype);
+  CUtensorMap ta, tb, tc;
   if (int rc = make_tmap_2d(&ta, a_q, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, uint64_t(k), uint64_t(m), uint64_t(k), BK, BM))
     return rc;
   if (int rc = make_tmap_2d(&tb, b_q, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, uint64_t(k), uint64_t(n), uint64_t(k), BK,
                             use_cluster ? BN / 2 : BN))
     return rc;
+  // output boxes of the TMA-store epilogue: one warp's 32 rows x 64 columns of T, or x 128 int8 codes (quantised output)
+  if (out_q != nullptr) {
+    if (int rc = make_tmap_2d(&tc, out_q, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, uint64_t(n), uint64_t(m), uint64_t(n), 128, 32))
+      return rc;
+  } else {
+    const CUtensorMapDataType t16 = c_dtype == TDB200_DTYPE_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+    if (int rc = make_tmap_2d(&tc, c, t16, 2, uint64_t(n), uint64_t(m), uint64_t(n) * 2, 64, 32)) return rc;
+  }
 
   GemmParams p;
   p.a_s = a_s;
@@ -555,13 +544,13 @@ static int gemm_impl(const int8_t* a_q, const float* a_s, const int8_t* b_q, con
   if (row_scale) {
     if (k > 16384 * 8) return fail(TDB200_ERR_UNSUPPORTED, "gemm_w8a8_rowwise: k too large for int32 accumulation");
     if (c_dtype == TDB200_DTYPE_BF16)
-      return use_cluster ? launch<__nv_bfloat16, true, true>(ta, tb, p, st) : launch<__nv_bfloat16, false, true>(ta, tb, p, st);
+      return use_cluster ? launch<__nv_bfloat16, true, true>(ta, tb, tc, p, st) : launch<__nv_bfloat16, false, true>(ta, tb, tc, p, st);
     if (c_dtype == TDB200_DTYPE_FP16)
-      return use_cluster ? launch<__half, true, true>(ta, tb, p, st) : launch<__half, false, true>(ta, tb, p, st);
+      return use_cluster ? launch<__half, true, true>(ta, tb, tc, p, st) : launch<__half, false, true>(ta, tb, tc, p, st);
   }
   if (c_dtype == TDB200_DTYPE_BF16)
-    return use_cluster ? launch<__nv_bfloat16, true, false>(ta, tb, p, st) : launch<__nv_bfloat16, false, false>(ta, tb, p, st);
+    return use_cluster ? launch<__nv_bfloat16, true, false>(ta, tb, tc, p, st) : launch<__nv_bfloat16, false, false>(ta, tb, tc, p, st);
   if (c_dtype == TDB200_DTYPE_FP16)
-    return use_cluster ? launch<__half, true, false>(ta, tb, p, st) : launch<__half, false, false>(ta, tb, p, st);
+    return use_cluster ? launch<__half, true, false>(ta, tb, tc, p, st) : launch<__half, false, false>(ta, tb, tc, p, st);
   return fail(TDB200_ERR_UNSUPPORTED, "gemm_w8a8: output dtype tag %d (bf16/fp16 only, gemm.cu:41-65)", c_dtype);
 }

@@ -2,6 +2,7 @@
 
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
@@ -73,8 +74,54 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
+// Encoded tensor maps are cached per thread: the denoise loop calls every operator with the same few hundred
+// (pointer, shape) combinations step after step (the caching allocator hands the same blocks back), and
+// cuTensorMapEncodeTiled costs about a microsecond per map on the launch path of eager callers.
+struct TmapKey {
+  uint64_t w[12];
+  bool operator==(const TmapKey& o) const { return memcmp(w, o.w, sizeof(w)) == 0; }
+};
+struct TmapSlot {
+  TmapKey key;
+  CUtensorMap map;
+  bool used;
+};
+static constexpr int kTmapSlots = 4096;  // direct-mapped
+static thread_local TmapSlot* g_tmap_cache = nullptr;
+
+static int encode_uncached(CUtensorMap* out, CUtensorMapDataType dtype, uint32_t rank, const void* base, const uint64_t* dims,
+                           const uint64_t* strides, const uint32_t* box);
+
 static int encode(CUtensorMap* out, CUtensorMapDataType dtype, uint32_t rank, const void* base, const uint64_t* dims,
                   const uint64_t* strides, const uint32_t* box) {
+  TmapKey k;
+  memset(&k, 0, sizeof(k));
+  k.w[0] = reinterpret_cast<uint64_t>(base);
+  k.w[1] = (uint64_t(dtype) << 32) | rank;
+  for (uint32_t i = 0; i < rank && i < 4; ++i) {
+    k.w[2 + i] = dims[i];
+    k.w[6 + i] = (i + 1 < rank) ? strides[i] : 0;
+    k.w[10 + (i >> 1)] |= uint64_t(box[i]) << (32 * (i & 1));
+  }
+  uint64_t h = 0x9E3779B97F4A7C15ull;
+  for (int i = 0; i < 12; ++i) h = (h ^ k.w[i]) * 0xFF51AFD7ED558CCDull + (h >> 29);
+  if (!g_tmap_cache) g_tmap_cache = static_cast<TmapSlot*>(calloc(kTmapSlots, sizeof(TmapSlot)));
+  TmapSlot* slot = g_tmap_cache ? &g_tmap_cache[(h >> 17) % kTmapSlots] : nullptr;
+  if (slot && slot->used && slot->key == k) {
+    memcpy(out, &slot->map, sizeof(CUtensorMap));
+    return 0;
+  }
+  if (int rc = encode_uncached(out, dtype, rank, base, dims, strides, box)) return rc;
+  if (slot) {
+    slot->key = k;
+    memcpy(&slot->map, out, sizeof(CUtensorMap));
+    slot->used = true;
+  }
+  return 0;
+}
+
+static int encode_uncached(CUtensorMap* out, CUtensorMapDataType dtype, uint32_t rank, const void* base, const uint64_t* dims,
+                           const uint64_t* strides, const uint32_t* box) {
   EncodeTiledFn fn = get_encode();
   if (!fn) return fail(TDB200_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
   if (!aligned16(base)) return fail(TDB200_ERR_INVALID_ARG, "TMA base address must be 16-byte aligned");
@@ -83,6 +130,16 @@ static int encode(CUtensorMap* out, CUtensorMapDataType dtype, uint32_t rank, co
                   reinterpret_cast<const cuuint64_t*>(strides), box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(TDB200_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return 0;
+}
+
+int set_max_dynamic_smem_once(const void* func, size_t bytes, bool* done_per_device, const char* what) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = -1;
+  if (dev >= 0 && done_per_device[dev]) return 0;
+  if (int rc = check_cuda(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes)), what))
+    return rc;
+  if (dev >= 0) done_per_device[dev] = true;
   return 0;
 }
 

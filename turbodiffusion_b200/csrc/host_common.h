@@ -34,6 +34,10 @@ int make_tmap_2d(CUtensorMap* out, const void* base, CUtensorMapDataType dtype, 
 int make_tmap_4d(CUtensorMap* out, const void* base, CUtensorMapDataType dtype, uint32_t elem_bytes,
                  const uint64_t dims[4], const uint64_t strides_bytes[3], const uint32_t box[4]);
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per device (`done_per_device`: a static bool[64] owned by the
+// caller, one per kernel instantiation, for kernels whose dynamic shared memory size is a compile-time constant).
+int set_max_dynamic_smem_once(const void* func, size_t bytes, bool* done_per_device, const char* what);
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 }  // namespace tdb

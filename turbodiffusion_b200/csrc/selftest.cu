@@ -145,3 +145,68 @@ extern "C" int tdb200_selftest_tmem_read(int warps, int iters, int convert, long
     tmem_read_probe_kernel<false><<<sm_count(), warps * 32, 0, st>>>(iters, cycles_per_cta, sink);
   return check_launch("tmem_read_probe_kernel");
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// XU (MUFU) throughput probe: every thread runs `iters` rounds of 8 independent chains of one transcendental.
+//   mode 0: ex2.approx.ftz.f32        1: ex2.approx.ftz.bf16x2      2: ex2.approx.f16x2
+//   mode 3: tanh.approx.f32           4: tanh.approx.bf16x2         5: tanh.approx.f16x2
+// Reports cycles per CTA (one CTA per SM, `warps` warps); results per clk per SM = warps*32*8*iters*(1 or 2)/cycles.
+// Decides whether the packed 16-bit forms deliver two results per XU issue slot (softmax / GELU epilogue design input).
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+template <int kMode>
+__global__ void __launch_bounds__(1024, 1) mufu_probe_kernel(int iters, long long* cycles, float* sink) {
+  uint32_t x[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float f = -0.001f * float(threadIdx.x + 1) - 0.01f * float(j);
+    if (kMode == 0 || kMode == 3) {
+      x[j] = __float_as_uint(f);
+    } else if (kMode == 1 || kMode == 4) {
+      __nv_bfloat162 v = __floats2bfloat162_rn(f, f * 0.5f);
+      x[j] = *reinterpret_cast<uint32_t*>(&v);
+    } else {
+      __half2 v = __floats2half2_rn(f, f * 0.5f);
+      x[j] = *reinterpret_cast<uint32_t*>(&v);
+    }
+  }
+  __syncthreads();
+  const long long t0 = clock64();
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (kMode == 0) asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+r"(x[j]));
+      if (kMode == 1) asm volatile("ex2.approx.ftz.bf16x2 %0, %0;" : "+r"(x[j]));
+      if (kMode == 2) asm volatile("ex2.approx.f16x2 %0, %0;" : "+r"(x[j]));
+      if (kMode == 3) asm volatile("tanh.approx.f32 %0, %0;" : "+r"(x[j]));
+      if (kMode == 4) asm volatile("tanh.approx.bf16x2 %0, %0;" : "+r"(x[j]));
+      if (kMode == 5) asm volatile("tanh.approx.f16x2 %0, %0;" : "+r"(x[j]));
+    }
+  }
+  __syncthreads();
+  const long long t1 = clock64();
+  uint32_t s = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s ^= x[j];
+  if (s == 0x12345678u) sink[0] = 1.f;
+  if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+}
+}  // namespace
+
+extern "C" int tdb200_selftest_mufu(int mode, int warps, int iters, long long* cycles_per_cta, float* sink, void* stream) {
+  using namespace tdb;
+  if (!cycles_per_cta || !sink || warps < 1 || warps > 32 || mode < 0 || mode > 5)
+    return fail(TDB200_ERR_INVALID_ARG, "selftest_mufu: mode in [0,5], warps in [1,32]");
+  if (int rc = require_sm100()) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int grid = sm_count();
+  switch (mode) {
+    case 0: mufu_probe_kernel<0><<<grid, warps * 32, 0, st>>>(iters, cycles_per_cta, sink); break;
+    case 1: mufu_probe_kernel<1><<<grid, warps * 32, 0, st>>>(iters, cycles_per_cta, sink); break;
+    case 2: mufu_probe_kernel<2><<<grid, warps * 32, 0, st>>>(iters, cycles_per_cta, sink); break;
+    case 3: mufu_probe_kernel<3><<<grid, warps * 32, 0, st>>>(iters, cycles_per_cta, sink); break;
+    case 4: mufu_probe_kernel<4><<<grid, warps * 32, 0, st>>>(iters, cycles_per_cta, sink); break;
+    default: mufu_probe_kernel<5><<<grid, warps * 32, 0, st>>>(iters, cycles_per_cta, sink); break;
+  }
+  return check_launch("mufu_probe_kernel");
+}

@@ -21,41 +21,7 @@
 #include "common.cuh"
 #include "host_common.h"
 
-// Build-time experiment switch (default 0 = the measured round-1 kernel):
-//   TDB200_NVCC_DEFINES="-DTDB_ATTN_POLY_EXP2=1" python -m turbodiffusion_b200._build --force
-// evaluates half of the softmax exponentials (the S columns 32..63 of each row) with a degree-3 polynomial on the FMA
-// pipe (packed f32x2) instead of MUFU.EX2, the FlashAttention-4 trick: the kernel is bound by the 16-lane/clk XU pipe
-// (8192 ex2 per 128x64 block), the FMA pipe is ~20 % busy.  |rel err| <= 7.5e-5, far below the 2^-9 rounding of P to 16 bit.
-#ifndef TDB_ATTN_POLY_EXP2
-#define TDB_ATTN_POLY_EXP2 0
-#endif
-// -DTDB_ATTN_P_TMEM=1: P(j) is written with tcgen05.st into the first 32 columns of the S buffer it was computed from
-// (S(j) already lives in registers) and P.V reads its A operand from tensor memory (tcgen05.mma [d], [a_tmem], b_desc).
-// That removes the 16 KB st.shared + fence.proxy.async publish; the in-order tensor pipe keeps Q.K^T(j+2) behind P.V(j),
-// which is what makes the aliasing safe (the MMA warp issues P.V(j) first).
-#ifndef TDB_ATTN_P_TMEM
-#define TDB_ATTN_P_TMEM 0
-#endif
-
 namespace {
-#if TDB_ATTN_POLY_EXP2
-// 2^x for x in [-125, 8]: n = rint(x) through the 1.5*2^23 magic add, f = x - n in [-0.5, 0.5], 2^f by a minimax cubic
-// (Lawson-weighted fit of the relative error), exponent patched in with one shift-add.
-__device__ __forceinline__ float2 poly_exp2_x2(float2 x) {
-  x.x = fmaxf(x.x, -125.0f);
-  x.y = fmaxf(x.y, -125.0f);
-  const float2 r = __fadd2_rn(x, make_float2(12582912.0f, 12582912.0f));
-  const float2 nf = __fadd2_rn(r, make_float2(-12582912.0f, -12582912.0f));
-  const float2 f = __ffma2_rn(nf, make_float2(-1.0f, -1.0f), x);
-  float2 p = __ffma2_rn(f, make_float2(0x1.c3f75ep-5f, 0x1.c3f75ep-5f), make_float2(0x1.f0de1ap-3f, 0x1.f0de1ap-3f));
-  p = __ffma2_rn(p, f, make_float2(0x1.62f31ap-1f, 0x1.62f31ap-1f));
-  p = __ffma2_rn(p, f, make_float2(0x1.fff692p-1f, 0x1.fff692p-1f));
-  float2 o;
-  o.x = __int_as_float(__float_as_int(p.x) + (__float_as_int(r.x) << 23));
-  o.y = __int_as_float(__float_as_int(p.y) + (__float_as_int(r.y) << 23));
-  return o;
-}
-#endif
 using namespace tdb;
 
 constexpr int D = 128;
@@ -210,18 +176,10 @@ sla_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q8, const __grid_co
         mbar_wait(&bars[kBarVFull + st], (i / kStages) & 1);
         tc_fence_after_sync();
         const uint64_t vdesc = make_desc_mnmajor_sw128(sbase + kOffV + st * kVBytes, kVBytes / 2);
-#if TDB_ATTN_P_TMEM
 #pragma unroll
         for (int ks = 0; ks < BLKK / 16; ++ks)  // K=16 keys per MMA: P +8 TMEM columns, V +16 rows (2048 B)
           umma_f16_ts(tmem_base + kColO, tmem_base + kColS + uint32_t(i & 1) * BLKK + uint32_t(ks * 8),
                       vdesc + uint64_t(ks * 128), id_pv, (i > 0 || ks > 0) ? 1u : 0u);
-#else
-        const uint64_t pdesc = make_desc_kmajor_sw128(sbase + kOffP);
-#pragma unroll
-        for (int ks = 0; ks < BLKK / 16; ++ks)  // K=16 keys per MMA: P +32 B in its row, V +16 rows (2048 B)
-          umma_f16_ss(tmem_base + kColO, pdesc + uint64_t(ks * 2), vdesc + uint64_t(ks * 128), id_pv,
-                      (i > 0 || ks > 0) ? 1u : 0u);
-#endif
         umma_commit(&bars[kBarVEmpty + st]);
         umma_commit(&bars[kBarPEmpty]);
         umma_commit(&bars[kBarPvDone]);
@@ -360,13 +318,8 @@ sla_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q8, const __grid_co
                                            __int_as_float(static_cast<int>(s1[c + 3]) + kMagicI)), sc2, cb2);
         t0.x = fast_exp2(t0.x); t0.y = fast_exp2(t0.y);
         t1.x = fast_exp2(t1.x); t1.y = fast_exp2(t1.y);
-#if TDB_ATTN_POLY_EXP2
-        t2 = poly_exp2_x2(t2);
-        t3 = poly_exp2_x2(t3);
-#else
         t2.x = fast_exp2(t2.x); t2.y = fast_exp2(t2.y);
         t3.x = fast_exp2(t3.x); t3.y = fast_exp2(t3.y);
-#endif
         psa = __fadd2_rn(psa, t0);
         psb = __fadd2_rn(psb, t1);
         psc = __fadd2_rn(psc, t2);
@@ -399,7 +352,6 @@ sla_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q8, const __grid_co
         tmem_ld_x32(tn + 32, s1);
       }
 
-#if TDB_ATTN_P_TMEM
       // ---- P row -> tensor memory: 32 packed columns over the S buffer this block was read from.  The wait for P.V(j-1)
       //      stays: the parity waits on kBarPvDone / kBarPEmpty are only unambiguous while the softmax warps run at most
       //      one P.V ahead of the tensor pipe (two ahead would alias the phase bit in the lazy-rescale wait above).
@@ -410,19 +362,6 @@ sla_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q8, const __grid_co
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars[kBarPFull]);
-#else
-      // ---- P row -> shared memory, K-major SW128: 16-byte chunk c of row r lives at r*128 + ((c ^ (r & 7)) << 4)
-      mbar_wait(&bars[kBarPEmpty], (j & 1) ^ 1);     // P.V of block j-1 has finished reading the (single) P buffer
-      TDB_TRACE(tracing, j, 5);
-      uint8_t* prow = sP + r * 128;
-#pragma unroll
-      for (int c = 0; c < 8; ++c)
-        *reinterpret_cast<uint4*>(prow + ((c ^ (r & 7)) << 4)) =
-            make_uint4(pw[4 * c], pw[4 * c + 1], pw[4 * c + 2], pw[4 * c + 3]);
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bars[kBarPFull]);
-#endif
       TDB_TRACE(tracing, j, 6);
     }
     if (tracing) trace_base[63 * 8 + 7] = clock64();  // loop exit

@@ -227,8 +227,9 @@ extern "C" int tdb200_sla_linear_moments(const void* k, const void* v, int dtype
   cudaStream_t st = static_cast<cudaStream_t>(stream);
 #define TDB_MOM(T)                                                                                                  \
   do {                                                                                                              \
-    if (int rc = check_cuda(cudaFuncSetAttribute(sla_moments_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                                 static_cast<int>(kSmemBytes)), "cudaFuncSetAttribute(sla_moments)")) \
+    static bool attr_done[64] = {false};                                                                            \
+    if (int rc = set_max_dynamic_smem_once(reinterpret_cast<const void*>(sla_moments_kernel<T>), kSmemBytes, attr_done, \
+                                           "cudaFuncSetAttribute(sla_moments)"))                                   \
       return rc;                                                                                                    \
     sla_moments_kernel<T><<<grid, kThreads, kSmemBytes, st>>>(tv, p);                                               \
     return check_launch("sla_moments_kernel");                                                                      \

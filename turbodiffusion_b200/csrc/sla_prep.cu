@@ -161,7 +161,9 @@ int run_k(const void* k, int64_t b, int64_t l, int64_t h, float* kmean, int8_t* 
           cudaStream_t st) {
   const int nblk = static_cast<int>(cdiv64(l, 64));
   const int chunks = static_cast<int>(cdiv64(l, kMeanRows));
-  float* partial = reinterpret_cast<float*>(k_i8);  // scratch: chunks*D*4 bytes per head <= l*D bytes (l*D/64 floats)
+  // scratch for the partial column sums: chunks*D floats per head.  They fit in the not-yet-written k_i8 buffer (l*D bytes
+  // per head) whenever 4*chunks <= l, i.e. l >= 4; a single chunk (l <= 256) reduces in place in the kmean output itself.
+  float* partial = chunks == 1 ? kmean : reinterpret_cast<float*>(k_i8);
   dim3 g1(static_cast<unsigned>(h), chunks, static_cast<unsigned>(b));
   kmean_partial_kernel<T, D><<<g1, 256, 0, st>>>(static_cast<const T*>(k), partial, l, static_cast<int>(h), chunks);
   if (int rc = check_launch("kmean_partial_kernel")) return rc;

@@ -180,6 +180,20 @@ class FastLayerNorm(nn.Module):
 
 
 # ------------------------------------------------------------------------------------------------ fused entry points
+def _f32(t: Optional[torch.Tensor], n: int, what: str) -> Optional[torch.Tensor]:
+    """Side inputs of the fused kernels (norm weights, modulation vectors, gates, angle tables) are read through raw fp32
+    pointers.  Checkpoints loaded with load_state_dict(assign=True) keep the checkpoint dtype (often bf16), so coerce to
+    contiguous fp32 here (a no-op for fp32 contiguous tensors) and check the element count."""
+    if t is None:
+        return None
+    require_cuda(t)
+    if t.dtype != torch.float32 or not t.is_contiguous():
+        t = t.float().contiguous()
+    if t.numel() != n:
+        raise ValueError(f"{what}: expected {n} elements, got {tuple(t.shape)}")
+    return t
+
+
 def _rows16(x: torch.Tensor):
     require_cuda(x)
     if x.dtype not in DTYPE_TAG:
@@ -217,6 +231,7 @@ def layernorm_modulate(x: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor
     """(norm(x).float() * (1 + scale) + shift).type_as(x)  — rcm/networks/wan2pt1.py:404, scale/shift fp32 [dim]."""
     x2 = _rows16(x)
     assert x2 is not None, "layernorm_modulate expects a bf16/fp16 input"
+    scale, shift = _f32(scale, x2.shape[1], "layernorm_modulate scale"), _f32(shift, x2.shape[1], "layernorm_modulate shift")
     y = torch.empty_like(x2)
     check(lib().tdb200_layer_norm_modulate(ptr(x2), DTYPE_TAG[x.dtype], ptr(scale), ptr(shift), ptr(y), x2.shape[0],
                                            x2.shape[1], float(eps), stream_ptr(x.device)), "layernorm_modulate")
@@ -228,6 +243,7 @@ def layernorm_modulate_quant(x: torch.Tensor, scale: torch.Tensor, shift: torch.
     x2 = _rows16(x)
     assert x2 is not None
     m, n = x2.shape
+    scale, shift = _f32(scale, n, "layernorm_modulate_quant scale"), _f32(shift, n, "layernorm_modulate_quant shift")
     q = torch.empty((m, n), dtype=torch.int8, device=x.device)
     s = torch.empty((cdiv(m, 128), cdiv(n, 128)), dtype=torch.float32, device=x.device)
     stats = torch.empty((2 * m,), dtype=torch.float32, device=x.device)
@@ -240,6 +256,7 @@ def layernorm_modulate_quant(x: torch.Tensor, scale: torch.Tensor, shift: torch.
 def gate_residual(x: torch.Tensor, y: torch.Tensor, gate: torch.Tensor) -> torch.Tensor:
     """x + y * gate.type_as(x)  — rcm/networks/wan2pt1.py:405-406, gate fp32 [dim]."""
     x2, y2 = _rows16(x), _rows16(y)
+    gate = _f32(gate, x2.shape[1], "gate_residual gate")
     out = torch.empty_like(x2)
     check(lib().tdb200_gate_residual(ptr(x2), ptr(y2), ptr(gate), ptr(out), DTYPE_TAG[x.dtype], x2.shape[0],
                                      x2.shape[1], stream_ptr(x.device)), "gate_residual")
@@ -249,6 +266,7 @@ def gate_residual(x: torch.Tensor, y: torch.Tensor, gate: torch.Tensor) -> torch
 def gate_residual_stats(x: torch.Tensor, y: torch.Tensor, gate: Optional[torch.Tensor], eps: float):
     """(x + y * gate.type_as(x)  [gate None: x + y],  row statistics of that result for the next LayerNorm)."""
     x2, y2 = _rows16(x), _rows16(y)
+    gate = _f32(gate, x2.shape[1], "gate_residual_stats gate")
     out = torch.empty_like(x2)
     stats = torch.empty((2 * x2.shape[0],), dtype=torch.float32, device=x.device)
     check(lib().tdb200_gate_residual_stats(ptr(x2), ptr(y2), ptr(gate), ptr(out), ptr(stats), DTYPE_TAG[x.dtype],
@@ -260,6 +278,8 @@ def layernorm_modulate_quant_from_stats(x: torch.Tensor, stats: torch.Tensor, sc
     """The tile pass of layernorm_modulate_quant with precomputed row statistics (from gate_residual_stats)."""
     x2 = _rows16(x)
     m, n = x2.shape
+    scale, shift = _f32(scale, n, "layernorm_modulate_quant_from_stats scale"), _f32(shift, n, "layernorm_modulate_quant_from_stats shift")
+    stats = _f32(stats, 2 * m, "layernorm_modulate_quant_from_stats stats")
     q = torch.empty((m, n), dtype=torch.int8, device=x.device)
     s = torch.empty((cdiv(m, 128), cdiv(n, 128)), dtype=torch.float32, device=x.device)
     check(lib().tdb200_layer_norm_modulate_quant_stats(ptr(x2), DTYPE_TAG[x.dtype], ptr(stats), ptr(scale), ptr(shift),
@@ -276,6 +296,7 @@ def rope_interleaved(x: torch.Tensor, angles: torch.Tensor) -> torch.Tensor:
     y = torch.empty_like(xc)
     rows = xc.numel() // (h * d)
     assert rows == angles.shape[0], "one angle row per token row"
+    angles = _f32(angles, rows * (d // 2), "rope_interleaved angles")
     check(lib().tdb200_rope_interleaved(ptr(xc), DTYPE_TAG[x.dtype], ptr(angles), ptr(y), rows, h, d,
                                         stream_ptr(x.device)), "rope_interleaved")
     return y
@@ -286,6 +307,8 @@ def rmsnorm_rope(x: torch.Tensor, w: torch.Tensor, angles: torch.Tensor, eps: fl
     require_cuda(x, w, angles)
     xc = x.contiguous()
     l, hd = xc.shape
+    w = _f32(w, hd, "rmsnorm_rope weight")
+    angles = _f32(angles, l * (hd // heads // 2), "rmsnorm_rope angles")
     y = torch.empty_like(xc)
     check(lib().tdb200_rms_norm_rope(ptr(xc), DTYPE_TAG[x.dtype], ptr(w), ptr(angles), ptr(y), l, heads, hd // heads,
                                      float(eps), stream_ptr(x.device)), "rmsnorm_rope")
