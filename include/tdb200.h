@@ -162,10 +162,21 @@ int tdb200_sla_block_map(const void* q_pool, const void* k_pool, int dtype, int6
                          int64_t nblk, int64_t d, int64_t topk, int8_t* sparse_map, int32_t* lut, void* stream);
 int tdb200_sla_linear_moments(const void* k, const void* v, int dtype, int64_t b, int64_t l, int64_t h, int64_t d,
                               float* kv, float* ksum, void* stream);
+/* Same with the feature map of the linear branch selectable (0 softmax, 1 elu+1, 2 relu; SLA/core.py:57-73) and head dim
+ * 64 or 128 (kv [b,h,d,d], ksum [b,h,d]). */
+int tdb200_sla_linear_moments_ex(const void* k, const void* v, int dtype, int64_t b, int64_t l, int64_t h, int64_t d,
+                                 int feature, float* kv, float* ksum, void* stream);
 int tdb200_sla_attn_fwd(const int8_t* q_i8, const float* q_scale, const int8_t* k_i8, const float* k_scale,
                         const void* v, const void* q, int dtype, const int32_t* lut, int64_t topk, const void* kvw,
                         const float* ksum, const float* proj_b, void* out, int64_t b, int64_t l, int64_t lk,
                         int64_t h, int64_t d, float sm_scale, void* stream);
+/* Second-generation fused kernel (persistent tiles, two softmax threads per query row, linear branch folded into the
+ * P.V accumulator); same arguments plus `feature`: 0 softmax, 1 elu+1, 2 relu feature map of the linear branch
+ * (SLA/core.py:57-73; the moments must have been built with the same map). */
+int tdb200_sla_attn_fwd_v2(const int8_t* q_i8, const float* q_scale, const int8_t* k_i8, const float* k_scale,
+                           const void* v, const void* q, int dtype, const int32_t* lut, int64_t topk, const void* kvw,
+                           const float* ksum, const float* proj_b, void* out, int64_t b, int64_t l, int64_t lk,
+                           int64_t h, int64_t d, float sm_scale, int feature, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * a12. LTX-2 (TurboT2AV) prologue variants   (ltx_core/model/transformer/transformer.py:21-94; Triton fast path

@@ -9,6 +9,8 @@ Inputs are consumed in place in their [B, L, H, D] layout; no transposed copies 
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -30,13 +32,33 @@ def linear_moments(k: torch.Tensor, v: torch.Tensor):
     return kv, ksum
 
 
-def attn_fwd(prep, v, q, lut, topk, kvw, ksum, proj_b, sm_scale, lk=None):
+ATTN_IMPL = os.environ.get("TDB200_ATTN_IMPL", "v2")  # "v1": one CTA per query block (round 1); "v2": persistent kernel
+
+
+ATTN_TIMER = None  # bench.py installs a callable(h, mblk, topk, d) -> context manager to time the fused-attention launches
+
+
+def attn_fwd(prep, v, q, lut, topk, kvw, ksum, proj_b, sm_scale, lk=None, impl=None, feature=0):
+    if ATTN_TIMER is not None:
+        with ATTN_TIMER(q.shape[2] * q.shape[0], (q.shape[1] + 127) // 128, topk, q.shape[3]):
+            return _attn_fwd(prep, v, q, lut, topk, kvw, ksum, proj_b, sm_scale, lk, impl, feature)
+    return _attn_fwd(prep, v, q, lut, topk, kvw, ksum, proj_b, sm_scale, lk, impl, feature)
+
+
+def _attn_fwd(prep, v, q, lut, topk, kvw, ksum, proj_b, sm_scale, lk=None, impl=None, feature=0):
     b, l, h, d = q.shape
     lk = v.shape[1] if lk is None else lk
     out = torch.empty_like(q)
-    check(lib().tdb200_sla_attn_fwd(ptr(prep.q_i8), ptr(prep.q_scale), ptr(prep.k_i8), ptr(prep.k_scale), ptr(v),
-                                    ptr(q), DTYPE_TAG[q.dtype], ptr(lut), topk, ptr(kvw), ptr(ksum), ptr(proj_b),
-                                    ptr(out), b, l, lk, h, d, float(sm_scale), stream_ptr(q.device)), "sla_attn_fwd")
+    if (impl or ATTN_IMPL) == "v1":
+        assert feature == 0
+        check(lib().tdb200_sla_attn_fwd(ptr(prep.q_i8), ptr(prep.q_scale), ptr(prep.k_i8), ptr(prep.k_scale), ptr(v),
+                                        ptr(q), DTYPE_TAG[q.dtype], ptr(lut), topk, ptr(kvw), ptr(ksum), ptr(proj_b),
+                                        ptr(out), b, l, lk, h, d, float(sm_scale), stream_ptr(q.device)), "sla_attn_fwd")
+    else:
+        check(lib().tdb200_sla_attn_fwd_v2(ptr(prep.q_i8), ptr(prep.q_scale), ptr(prep.k_i8), ptr(prep.k_scale), ptr(v),
+                                           ptr(q), DTYPE_TAG[q.dtype], ptr(lut), topk, ptr(kvw), ptr(ksum), ptr(proj_b),
+                                           ptr(out), b, l, lk, h, d, float(sm_scale), feature, stream_ptr(q.device)),
+              "sla_attn_fwd")
     return out
 
 

@@ -210,6 +210,16 @@ __device__ __forceinline__ uint64_t make_desc_kmajor_sw128(uint32_t smem_addr) {
 __device__ __forceinline__ uint64_t make_desc_mnmajor_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
   return make_smem_desc(smem_addr, lbo_bytes, 1024);
 }
+// K-major, SWIZZLE_64B: rows of exactly 64 bytes of K (e.g. 64 int8), 8-row groups of 512 bytes -> SBO = 512.
+constexpr uint64_t kDescSwizzle64B = 4ull << 61;
+__device__ __forceinline__ uint64_t make_desc_kmajor_sw64(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>((512u >> 4) & 0x3FFFu) << 32;
+  d |= kDescVersionSm100 | kDescSwizzle64B;
+  return d;
+}
 
 // Instruction descriptor (32 bit), dense, no negate/saturate:
 //   [4,6) D format (0 f16, 1 f32, 2 s32)   [7,10) A format   [10,13) B format

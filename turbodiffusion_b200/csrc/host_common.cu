@@ -90,14 +90,14 @@ static constexpr int kTmapSlots = 4096;  // direct-mapped
 static thread_local TmapSlot* g_tmap_cache = nullptr;
 
 static int encode_uncached(CUtensorMap* out, CUtensorMapDataType dtype, uint32_t rank, const void* base, const uint64_t* dims,
-                           const uint64_t* strides, const uint32_t* box);
+                           const uint64_t* strides, const uint32_t* box, int swizzle_bytes);
 
 static int encode(CUtensorMap* out, CUtensorMapDataType dtype, uint32_t rank, const void* base, const uint64_t* dims,
-                  const uint64_t* strides, const uint32_t* box) {
+                  const uint64_t* strides, const uint32_t* box, int swizzle_bytes = 128) {
   TmapKey k;
   memset(&k, 0, sizeof(k));
   k.w[0] = reinterpret_cast<uint64_t>(base);
-  k.w[1] = (uint64_t(dtype) << 32) | rank;
+  k.w[1] = (uint64_t(dtype) << 32) | (uint64_t(swizzle_bytes) << 8) | rank;
   for (uint32_t i = 0; i < rank && i < 4; ++i) {
     k.w[2 + i] = dims[i];
     k.w[6 + i] = (i + 1 < rank) ? strides[i] : 0;
@@ -111,7 +111,7 @@ static int encode(CUtensorMap* out, CUtensorMapDataType dtype, uint32_t rank, co
     memcpy(out, &slot->map, sizeof(CUtensorMap));
     return 0;
   }
-  if (int rc = encode_uncached(out, dtype, rank, base, dims, strides, box)) return rc;
+  if (int rc = encode_uncached(out, dtype, rank, base, dims, strides, box, swizzle_bytes)) return rc;
   if (slot) {
     slot->key = k;
     memcpy(&slot->map, out, sizeof(CUtensorMap));
@@ -121,14 +121,15 @@ static int encode(CUtensorMap* out, CUtensorMapDataType dtype, uint32_t rank, co
 }
 
 static int encode_uncached(CUtensorMap* out, CUtensorMapDataType dtype, uint32_t rank, const void* base, const uint64_t* dims,
-                           const uint64_t* strides, const uint32_t* box) {
+                           const uint64_t* strides, const uint32_t* box, int swizzle_bytes) {
   EncodeTiledFn fn = get_encode();
   if (!fn) return fail(TDB200_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
   if (!aligned16(base)) return fail(TDB200_ERR_INVALID_ARG, "TMA base address must be 16-byte aligned");
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUresult r = fn(out, dtype, rank, const_cast<void*>(base), reinterpret_cast<const cuuint64_t*>(dims),
                   reinterpret_cast<const cuuint64_t*>(strides), box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(TDB200_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
   return 0;
 }
@@ -155,11 +156,12 @@ int make_tmap_2d(CUtensorMap* out, const void* base, CUtensorMapDataType dtype, 
 }
 
 int make_tmap_4d(CUtensorMap* out, const void* base, CUtensorMapDataType dtype, uint32_t elem_bytes,
-                 const uint64_t dims[4], const uint64_t strides_bytes[3], const uint32_t box[4]) {
-  if (box[0] * elem_bytes > 128) return fail(TDB200_ERR_INVALID_ARG, "TMA inner box exceeds 128 bytes");
+                 const uint64_t dims[4], const uint64_t strides_bytes[3], const uint32_t box[4], int swizzle_bytes) {
+  if (swizzle_bytes != 64 && swizzle_bytes != 128) return fail(TDB200_ERR_INVALID_ARG, "TMA swizzle must be 64 or 128 bytes");
+  if (box[0] * elem_bytes > uint32_t(swizzle_bytes)) return fail(TDB200_ERR_INVALID_ARG, "TMA inner box exceeds the swizzle span");
   for (int i = 0; i < 3; ++i)
     if (strides_bytes[i] % 16 != 0) return fail(TDB200_ERR_INVALID_ARG, "TMA strides must be multiples of 16 bytes");
-  return encode(out, dtype, 4, base, dims, strides_bytes, box);
+  return encode(out, dtype, 4, base, dims, strides_bytes, box, swizzle_bytes);
 }
 
 }  // namespace tdb

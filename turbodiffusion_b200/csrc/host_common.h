@@ -31,8 +31,9 @@ int make_tmap_2d(CUtensorMap* out, const void* base, CUtensorMapDataType dtype, 
                  uint64_t outer, uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer);
 
 // Rank-4 tiled tensor map; dims/strides listed innermost first (strides for dims 1..3, in bytes).
+// swizzle_bytes: 128 (default) or 64 (tiles whose rows are 64 bytes: int8 Q/K of 64-wide heads).
 int make_tmap_4d(CUtensorMap* out, const void* base, CUtensorMapDataType dtype, uint32_t elem_bytes,
-                 const uint64_t dims[4], const uint64_t strides_bytes[3], const uint32_t box[4]);
+                 const uint64_t dims[4], const uint64_t strides_bytes[3], const uint32_t box[4], int swizzle_bytes = 128);
 
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per device (`done_per_device`: a static bool[64] owned by the
 // caller, one per kernel instantiation, for kernels whose dynamic shared memory size is a compile-time constant).

@@ -110,18 +110,25 @@ struct RowParams {
 };
 
 // T: element type of x and y.  kChunks: 16-byte chunks per thread.
-template <typename T, int kNorm, int kPost, int kThreads, int kChunks, bool kResidIn = false>
+// kWarpRow = false: one CTA per row (reductions through shared memory, two __syncthreads each).
+// kWarpRow = true : one WARP per row, kThreads/32 rows per CTA: the reductions are shuffles only, no CTA barrier, and a
+//   lane keeps kChunks independent 16-byte loads in flight (6 for dim 1536, 20 for dim 5120), which is what an HBM-bound
+//   row kernel needs; round 1's CTA-per-row form reached 0.27-0.6 of the HBM peak.
+template <typename T, int kNorm, int kPost, int kThreads, int kChunks, bool kResidIn = false, bool kWarpRow = false>
 __global__ void __launch_bounds__(kThreads) row_norm_kernel(RowParams p) {
   __shared__ float red[kThreads / 32];
   constexpr int E = Chunk<T>::kElems;
-  const int64_t row = blockIdx.x;
+  constexpr int kStride = kWarpRow ? 32 : kThreads;
+  const int tix = kWarpRow ? int(threadIdx.x & 31) : int(threadIdx.x);
+  const int64_t row = kWarpRow ? int64_t(blockIdx.x) * (kThreads / 32) + (threadIdx.x >> 5) : int64_t(blockIdx.x);
+  if (kWarpRow && row >= p.m) return;  // whole warp leaves; there is no CTA-wide barrier in this form
   const int nchunks = p.n / E;
   const T* xr = static_cast<const T*>(p.x) + row * p.n;
 
   uint4 raw[kChunks];
 #pragma unroll
   for (int i = 0; i < kChunks; ++i) {
-    const int c = threadIdx.x + i * kThreads;
+    const int c = tix + i * kStride;
     raw[i] = make_uint4(0u, 0u, 0u, 0u);
     if (c < nchunks) raw[i] = ldg_nc_v4(xr + c * E);
   }
@@ -131,7 +138,7 @@ __global__ void __launch_bounds__(kThreads) row_norm_kernel(RowParams p) {
     T* out = static_cast<T*>(p.y) + row * p.n;
 #pragma unroll
     for (int i = 0; i < kChunks; ++i) {
-      const int c = threadIdx.x + i * kThreads;
+      const int c = tix + i * kStride;
       if (c < nchunks) {
         float xf[E], yf[E], gv[E];
         Chunk<T>::unpack(raw[i], xf);
@@ -159,7 +166,7 @@ __global__ void __launch_bounds__(kThreads) row_norm_kernel(RowParams p) {
 #pragma unroll
       for (int j = 0; j < E; ++j) ss = fmaf(f[j], f[j], ss);
     }
-    ss = block_sum<kThreads>(ss, red);
+    ss = kWarpRow ? warp_sum(ss) : block_sum<kThreads>(ss, red);
     rstd = 1.0f / sqrtf(__fadd_rn(ss / static_cast<float>(p.n), p.eps));
   } else {
     float s = 0.f;
@@ -170,12 +177,12 @@ __global__ void __launch_bounds__(kThreads) row_norm_kernel(RowParams p) {
 #pragma unroll
       for (int j = 0; j < E; ++j) s += f[j];
     }
-    s = block_sum<kThreads>(s, red);
+    s = kWarpRow ? warp_sum(s) : block_sum<kThreads>(s, red);
     mean = s / static_cast<float>(p.n);
     float ss = 0.f;
 #pragma unroll
     for (int i = 0; i < kChunks; ++i) {
-      const int c = threadIdx.x + i * kThreads;
+      const int c = tix + i * kStride;
       if (c < nchunks) {
         float f[E];
         Chunk<T>::unpack(raw[i], f);
@@ -186,7 +193,7 @@ __global__ void __launch_bounds__(kThreads) row_norm_kernel(RowParams p) {
         }
       }
     }
-    ss = block_sum<kThreads>(ss, red);
+    ss = kWarpRow ? warp_sum(ss) : block_sum<kThreads>(ss, red);
     // the reference's unmasked padding columns: (N2 - N) * mean^2
     ss = __fadd_rn(ss, __fmul_rn(static_cast<float>(next_pow2_dev(p.n) - p.n), __fmul_rn(mean, mean)));
     rstd = 1.0f / sqrtf(__fadd_rn(ss / static_cast<float>(p.n), p.eps));
@@ -194,7 +201,7 @@ __global__ void __launch_bounds__(kThreads) row_norm_kernel(RowParams p) {
   (void)inv_n;
 
   if (kPost == kPostStatsOnly) {
-    if (threadIdx.x == 0) {
+    if (tix == 0) {
       p.stats[2 * row] = mean;
       p.stats[2 * row + 1] = rstd;
     }
@@ -204,7 +211,7 @@ __global__ void __launch_bounds__(kThreads) row_norm_kernel(RowParams p) {
   T* yr = static_cast<T*>(p.y) + row * p.n;
 #pragma unroll
   for (int i = 0; i < kChunks; ++i) {
-    const int c = threadIdx.x + i * kThreads;
+    const int c = tix + i * kStride;
     if (c < nchunks) {
       float f[E];
       Chunk<T>::unpack(raw[i], f);
@@ -252,6 +259,22 @@ int launch_rows(const RowParams& p, cudaStream_t st) {
   constexpr int E = Chunk<T>::kElems;
   const int nchunks = p.n / E;
   if (p.m > 0x7FFFFFFFll) return fail(TDB200_ERR_UNSUPPORTED, "row kernel: too many rows");
+  // warp-per-row form for rows of up to 24 chunks per lane (n <= 6144 16-bit elements); 8 rows per 256-thread CTA
+  {
+    const unsigned wgrid = static_cast<unsigned>((p.m + 7) / 8);
+#define TDB_LAUNCH_W(CH)                                                                   \
+  row_norm_kernel<T, kNorm, kPost, 256, CH, kResidIn, true><<<wgrid, 256, 0, st>>>(p);    \
+  return check_launch("row_norm_kernel(warp)")
+    if (nchunks <= 32 * 2) { TDB_LAUNCH_W(2); }
+    if (nchunks <= 32 * 4) { TDB_LAUNCH_W(4); }
+    if (nchunks <= 32 * 6) { TDB_LAUNCH_W(6); }
+    if (nchunks <= 32 * 8) { TDB_LAUNCH_W(8); }
+    if (nchunks <= 32 * 12) { TDB_LAUNCH_W(12); }
+    if (nchunks <= 32 * 16) { TDB_LAUNCH_W(16); }
+    if (nchunks <= 32 * 20) { TDB_LAUNCH_W(20); }
+    if (nchunks <= 32 * 24) { TDB_LAUNCH_W(24); }
+#undef TDB_LAUNCH_W
+  }
   const unsigned grid = static_cast<unsigned>(p.m);
 #define TDB_LAUNCH(TH, CH)                                                         \
   row_norm_kernel<T, kNorm, kPost, TH, CH, kResidIn><<<grid, TH, 0, st>>>(p);      \

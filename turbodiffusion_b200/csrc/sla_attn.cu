@@ -16,6 +16,8 @@
 //   transposed/quantised copy of V is ever materialised.
 // The O accumulator is only rescaled when a row maximum grows by more than 2^8 (lazy rescale): P stays <= 256, which
 // bf16/fp32 hold exactly as well as P <= 1, and the final O / l normalisation is unchanged.
+#include <stdlib.h>
+
 #include <type_traits>
 
 #include "common.cuh"
@@ -230,6 +232,7 @@ sla_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q8, const __grid_co
     long long* trace_base = nullptr;
     const bool tracing = g_attn_trace != nullptr && warp == 0 && lane == 0 && hh == 0 && b == 0 && (m_blk == 1 || m_blk == 3);
     if (tracing) trace_base = g_attn_trace + (m_blk == 1 ? 0 : 64 * 8);
+    if (tracing) trace_base[62 * 8 + 0] = clock64();   // row 62: tile-level marks (0 entry, 1 first S, 2 loop exit, 3 phi, 4 OL, 5 stores)
     float m_used = -INFINITY, l_sum = 0.f;
     // The S tile of block j+1 is pulled out of TMEM while P(j) is being published (Q.K^T runs one block ahead), so the
     // tcgen05.ld latency no longer sits in front of the row max.
@@ -238,6 +241,7 @@ sla_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q8, const __grid_co
     tc_fence_after_sync();
     tmem_ld_x32(tmem_base + lane_addr + kColS, s0);
     tmem_ld_x32(tmem_base + lane_addr + kColS + 32, s1);
+    if (tracing) trace_base[62 * 8 + 1] = clock64();
     for (int j = 0; j < T_blocks; ++j) {
       TDB_TRACE(tracing, j, 0);
       const int st = j & 1;
@@ -365,6 +369,7 @@ sla_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q8, const __grid_co
       TDB_TRACE(tracing, j, 6);
     }
     if (tracing) trace_base[63 * 8 + 7] = clock64();  // loop exit
+    if (tracing) trace_base[62 * 8 + 2] = clock64();
 
     // ---- linear branch operand: phi(q) = softmax over D of this thread's query row (SLA/core.py:243), rounded to T
     float den = 1e-5f;
@@ -421,10 +426,12 @@ sla_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q8, const __grid_co
     fence_proxy_async_smem();
     __syncwarp();
     if (lane == 0) mbar_arrive(&bars[kBarPhiFull]);
+    if (tracing) trace_base[62 * 8 + 3] = clock64();
 
     // ---- merge: out = T( O / l + OL / den + proj_b )
     mbar_wait(&bars[kBarOlFull], 0);
     tc_fence_after_sync();
+    if (tracing) trace_base[62 * 8 + 4] = clock64();
     const float inv_l = 1.0f / l_sum, inv_den = 1.0f / den;
     // Staging: rows 0-63 in the P buffer, rows 64-127 in the Q tile (both free once the linear MMA has retired); 256-byte
     // rows, 16-byte chunk c of row r at (c ^ (r & 15)).  Each warp then writes its own 32 rows, two full rows per
@@ -467,6 +474,7 @@ sla_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q8, const __grid_co
           stg_v4(static_cast<T*>(p.out) + ((int64_t(b) * p.l + grow) * p.h + hh) * D + cc * 8, v4);
       }
     }
+    if (tracing) trace_base[62 * 8 + 5] = clock64();
     tc_fence_before_sync();
   }
 
@@ -496,7 +504,8 @@ extern "C" int tdb200_sla_attn_fwd(const int8_t* q_i8, const float* q_scale, con
   if (topk <= 0 || topk > nblk) return fail(TDB200_ERR_INVALID_ARG, "sla_attn_fwd: topk=%lld outside [1, %lld]", (long long)topk, (long long)nblk);
   if (nblk > 65535 || h > 65535 || b > 65535) return fail(TDB200_ERR_UNSUPPORTED, "sla_attn_fwd: dimension too large");
   const size_t lut_bytes = ((size_t(topk) * 2 + 15) & ~size_t(15)) + size_t(topk) * 4;
-  const size_t smem = 1024 + kOffLut + lut_bytes;
+  static const bool one_cta_per_sm = getenv("TDB200_ATTN_ONE_CTA_PER_SM") != nullptr;  // diagnostics: timeline without a sibling CTA
+  const size_t smem = 1024 + kOffLut + lut_bytes + (one_cta_per_sm ? 64 * 1024 : 0);
   if (smem > 227 * 1024) return fail(TDB200_ERR_UNSUPPORTED, "sla_attn_fwd: topk=%lld too large for on-chip LUT", (long long)topk);
   if (int rc = require_sm100()) return rc;
 

@@ -9,6 +9,11 @@
 // phi(k) into shared memory in the MN-major 128B-swizzled operand layout, then column-sum the tile for ksum.
 // warp 4: TMA loads of the V tile (consumed MN-major as the A operand: M = value channel).  warp 5: tcgen05.mma
 // kind::f16, D[128(dv) x 128(dk)] += V^T . phi(K), fp32 accumulator in TMEM across all tiles of this CTA.
+// 64-wide heads (SLA/core.py:207) run through the same 128x128 tile as PAIRS of adjacent heads: in the [L, H, 64] layout two
+// heads are 128 contiguous columns, i.e. exactly one 128-wide row of V and of K.  The tensor core then produces
+// [V_a | V_b]^T . [phi(K_a) | phi(K_b)]; its two diagonal 64x64 blocks are the two heads' moment matrices (the off-diagonal
+// blocks are discarded), so a pair costs what one 128-wide head costs.  phi is evaluated per 64-wide half.
+// Feature maps (SLA/core.py:57-73): 0 softmax over the head dim, 1 elu(x)+1, 2 relu(x).
 #include <type_traits>
 
 #include "common.cuh"
@@ -35,6 +40,8 @@ struct MomParams {
   float* kv;
   float* ksum;
   int l, h, tiles, splits;
+  int hd;        // 128, or 64 (two heads per 128-wide row; `h` is then the number of REAL heads, grid.x = ceil(h/2) pairs)
+  int feature;   // 0 softmax, 1 elu+1, 2 relu
 };
 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
@@ -49,8 +56,11 @@ sla_moments_kernel(const __grid_constant__ CUtensorMap tmap_v, MomParams p) {
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBars);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kNumBars);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int hh = blockIdx.x, split = blockIdx.y, b = blockIdx.z;  // heads fastest (DRAM page locality of [L, H, D])
-  const int bh = b * p.h + hh;
+  const int hh = blockIdx.x, split = blockIdx.y, b = blockIdx.z;  // heads (or head pairs) fastest: DRAM page locality of [L, H, D]
+  const bool pair = p.hd == 64;
+  const int head0 = pair ? 2 * hh : hh;                            // first real head of this CTA
+  const bool second_ok = !pair || head0 + 1 < p.h;                 // odd head count: the last pair has one real head
+  const int64_t row_elems = int64_t(p.h) * p.hd;                   // elements per token row of k / v
   const int my_tiles = (p.tiles - split + p.splits - 1) / p.splits;  // tiles split, split+splits, ...
 
   if (threadIdx.x == 0) {
@@ -81,8 +91,10 @@ sla_moments_kernel(const __grid_constant__ CUtensorMap tmap_v, MomParams p) {
         mbar_wait(&bars[kStageEmpty + st], ((i >> 1) & 1) ^ 1);
         mbar_expect_tx(&bars[kVFull + st], kOperandBytes);
         uint8_t* sv = smem + kOffV + st * kOperandBytes;
-        tma_load_4d(sv, &tmap_v, &bars[kVFull + st], 0, hh, tile * kRowsPerTile, b);
-        tma_load_4d(sv + kBlockBytes, &tmap_v, &bars[kVFull + st], 64, hh, tile * kRowsPerTile, b);
+        // 128-wide head: columns [0,64) and [64,128) of head hh; 64-wide heads: heads 2hh and 2hh+1 (a missing second
+        // head is out of range in the head dimension, which TMA fills with zeros)
+        tma_load_4d(sv, &tmap_v, &bars[kVFull + st], 0, head0, tile * kRowsPerTile, b);
+        tma_load_4d(sv + kBlockBytes, &tmap_v, &bars[kVFull + st], pair ? 0 : 64, pair ? head0 + 1 : head0, tile * kRowsPerTile, b);
       }
     }
   } else if (warp == 5) {
@@ -112,32 +124,45 @@ sla_moments_kernel(const __grid_constant__ CUtensorMap tmap_v, MomParams p) {
       const int64_t row = int64_t(tile) * kRowsPerTile + r;
       uint32_t w[D / 2];
       if (row < p.l) {
-        const uint4* src = reinterpret_cast<const uint4*>(static_cast<const T*>(p.k) + ((int64_t(b) * p.l + row) * p.h + hh) * D);
-        float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+        const uint4* src = reinterpret_cast<const uint4*>(static_cast<const T*>(p.k) + (int64_t(b) * p.l + row) * row_elems + int64_t(head0) * p.hd);
+        const int nload = second_ok ? D / 8 : D / 16;   // the second half belongs to the next (non-existent) head
 #pragma unroll
         for (int c = 0; c < D / 8; ++c) {
-          const uint4 raw = ldg_nc_v4(src + c);
+          uint4 raw = make_uint4(0u, 0u, 0u, 0u);
+          if (c < nload) raw = ldg_nc_v4(src + c);
           w[4 * c] = raw.x; w[4 * c + 1] = raw.y; w[4 * c + 2] = raw.z; w[4 * c + 3] = raw.w;
-          m0 = fmaxf(m0, fmaxf(F16Traits<T>::lo(raw.x), F16Traits<T>::hi(raw.x)));
-          m1 = fmaxf(m1, fmaxf(F16Traits<T>::lo(raw.y), F16Traits<T>::hi(raw.y)));
-          m2 = fmaxf(m2, fmaxf(F16Traits<T>::lo(raw.z), F16Traits<T>::hi(raw.z)));
-          m3 = fmaxf(m3, fmaxf(F16Traits<T>::lo(raw.w), F16Traits<T>::hi(raw.w)));
         }
-        const float mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-        const float off = mx * kLog2e;
-        float sa = 0.f, sb = 0.f, sc4 = 0.f, sd = 0.f;  // independent chains: the row softmax is latency-, not issue-bound
+        // phi over each `seg`-wide segment of the row (one segment for a 128-wide head, two for a pair of 64-wide heads)
 #pragma unroll
-        for (int q = 0; q < D / 2; q += 2) {
-          sa += fast_exp2(fmaf(F16Traits<T>::lo(w[q]), kLog2e, -off));
-          sb += fast_exp2(fmaf(F16Traits<T>::hi(w[q]), kLog2e, -off));
-          sc4 += fast_exp2(fmaf(F16Traits<T>::lo(w[q + 1]), kLog2e, -off));
-          sd += fast_exp2(fmaf(F16Traits<T>::hi(w[q + 1]), kLog2e, -off));
+        for (int sgm = 0; sgm < 2; ++sgm) {
+          if (!pair && sgm == 1) break;
+          const int w0 = pair ? sgm * (D / 4) : 0, w1 = pair ? (sgm + 1) * (D / 4) : D / 2;
+          if (p.feature == 0) {
+            float mx = -INFINITY;
+            for (int q = w0; q < w1; ++q) mx = fmaxf(mx, fmaxf(F16Traits<T>::lo(w[q]), F16Traits<T>::hi(w[q])));
+            const float off = mx * kLog2e;
+            float sa = 0.f, sb = 0.f;
+            for (int q = w0; q < w1; ++q) {
+              sa += fast_exp2(fmaf(F16Traits<T>::lo(w[q]), kLog2e, -off));
+              sb += fast_exp2(fmaf(F16Traits<T>::hi(w[q]), kLog2e, -off));
+            }
+            const float inv = 1.0f / (sa + sb);
+            for (int q = w0; q < w1; ++q)
+              w[q] = F16Traits<T>::pack(fast_exp2(fmaf(F16Traits<T>::lo(w[q]), kLog2e, -off)) * inv,
+                                       fast_exp2(fmaf(F16Traits<T>::hi(w[q]), kLog2e, -off)) * inv);
+          } else {
+            for (int q = w0; q < w1; ++q) {
+              const float a = F16Traits<T>::lo(w[q]), c = F16Traits<T>::hi(w[q]);
+              const float fa = p.feature == 1 ? (a > 0.f ? a + 1.0f : fast_exp2(a * kLog2e)) : fmaxf(a, 0.f);
+              const float fc = p.feature == 1 ? (c > 0.f ? c + 1.0f : fast_exp2(c * kLog2e)) : fmaxf(c, 0.f);
+              w[q] = F16Traits<T>::pack(fa, fc);
+            }
+          }
         }
-        const float inv = 1.0f / ((sa + sb) + (sc4 + sd));
+        if (!second_ok) {
 #pragma unroll
-        for (int q = 0; q < D / 2; ++q)
-          w[q] = F16Traits<T>::pack(fast_exp2(fmaf(F16Traits<T>::lo(w[q]), kLog2e, -off)) * inv,
-                                   fast_exp2(fmaf(F16Traits<T>::hi(w[q]), kLog2e, -off)) * inv);
+          for (int q = D / 4; q < D / 2; ++q) w[q] = 0u;
+        }
       } else {
 #pragma unroll
         for (int q = 0; q < D / 2; ++q) w[q] = 0u;
@@ -169,20 +194,43 @@ sla_moments_kernel(const __grid_constant__ CUtensorMap tmap_v, MomParams p) {
         ksum_acc += (s4[0] + s4[1]) + (s4[2] + s4[3]);
       }
     }
-    atomicAdd(p.ksum + int64_t(bh) * D + r, ksum_acc);
+    // thread r holds key channel r of the 128-wide row: head0's channel r, or (pairs) channel r-64 of head0+1
+    if (!pair) {
+      atomicAdd(p.ksum + (int64_t(b) * p.h + head0) * D + r, ksum_acc);
+    } else if (r < 64 || second_ok) {
+      atomicAdd(p.ksum + (int64_t(b) * p.h + head0 + (r >> 6)) * 64 + (r & 63), ksum_acc);
+    }
     // ---- kv: TMEM lane r = value channel r, 128 key channels
     mbar_wait(&bars[kAccFull], 0);
     tc_fence_after_sync();
-    float* dst = p.kv + (int64_t(bh) * D + r) * D;
+    if (!pair) {
+      float* dst = p.kv + ((int64_t(b) * p.h + head0) * D + r) * D;
 #pragma unroll
-    for (int c = 0; c < D / 32; ++c) {
-      uint32_t o[32];
-      tmem_ld_x32(tmem_base + (uint32_t(warp * 32) << 16) + c * 32, o);
-      tmem_ld_wait();
+      for (int c = 0; c < D / 32; ++c) {
+        uint32_t o[32];
+        tmem_ld_x32(tmem_base + (uint32_t(warp * 32) << 16) + c * 32, o);
+        tmem_ld_wait();
 #pragma unroll
-      for (int q = 0; q < 32; q += 4)
-        red_add_v4(dst + c * 32 + q, __uint_as_float(o[q]), __uint_as_float(o[q + 1]), __uint_as_float(o[q + 2]),
-                   __uint_as_float(o[q + 3]));
+        for (int q = 0; q < 32; q += 4)
+          red_add_v4(dst + c * 32 + q, __uint_as_float(o[q]), __uint_as_float(o[q + 1]), __uint_as_float(o[q + 2]),
+                     __uint_as_float(o[q + 3]));
+      }
+    } else {
+      // lane r = value channel (r & 63) of head0 + (r >> 6); its diagonal block is key columns [64*(r>>6), +64)
+      const int sub = r >> 6;                        // warp-uniform (warps 0,1 -> head0; warps 2,3 -> head0+1)
+      float* dst = p.kv + ((int64_t(b) * p.h + head0 + sub) * 64 + (r & 63)) * 64;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t o[32];
+        tmem_ld_x32(tmem_base + (uint32_t(warp * 32) << 16) + sub * 64 + c * 32, o);
+        tmem_ld_wait();
+        if (sub == 0 || second_ok) {
+#pragma unroll
+          for (int q = 0; q < 32; q += 4)
+            red_add_v4(dst + c * 32 + q, __uint_as_float(o[q]), __uint_as_float(o[q + 1]), __uint_as_float(o[q + 2]),
+                       __uint_as_float(o[q + 3]));
+        }
+      }
     }
     tc_fence_before_sync();
   }
@@ -195,12 +243,13 @@ sla_moments_kernel(const __grid_constant__ CUtensorMap tmap_v, MomParams p) {
 
 }  // namespace
 
-extern "C" int tdb200_sla_linear_moments(const void* k, const void* v, int dtype, int64_t b, int64_t l, int64_t h,
-                                         int64_t d, float* kv, float* ksum, void* stream) {
+static int moments_impl(const void* k, const void* v, int dtype, int64_t b, int64_t l, int64_t h, int64_t d, int feature,
+                        float* kv, float* ksum, void* stream) {
   using namespace tdb;
   if (!k || !v || !kv || !ksum) return fail(TDB200_ERR_INVALID_ARG, "sla_linear_moments: null pointer");
   if (b <= 0 || l <= 0 || h <= 0) return fail(TDB200_ERR_INVALID_ARG, "sla_linear_moments: bad shape");
-  if (d != D) return fail(TDB200_ERR_UNSUPPORTED, "sla_linear_moments: head dim %lld (this build implements d=128)", (long long)d);
+  if (d != 64 && d != 128) return fail(TDB200_ERR_UNSUPPORTED, "sla_linear_moments: head dim %lld (64 or 128, SLA/core.py:207)", (long long)d);
+  if (feature < 0 || feature > 2) return fail(TDB200_ERR_INVALID_ARG, "sla_linear_moments: feature map tag %d", feature);
   if (h > 65535 || b > 65535) return fail(TDB200_ERR_UNSUPPORTED, "sla_linear_moments: h or b too large");
   if (!aligned16(k) || !aligned16(kv)) return fail(TDB200_ERR_INVALID_ARG, "sla_linear_moments: buffers must be 16-byte aligned");
   if (int rc = require_sm100()) return rc;
@@ -212,18 +261,21 @@ extern "C" int tdb200_sla_linear_moments(const void* k, const void* v, int dtype
     const uint32_t box[4] = {64, 1, kRowsPerTile, 1};
     if (int rc = make_tmap_4d(&tv, v, t16, 2, dims, str, box)) return rc;
   }
+  const int64_t units = d == 128 ? h : cdiv64(h, 2);   // CTAs along x: heads, or pairs of 64-wide heads
   MomParams p;
   p.k = k;
   p.kv = kv;
   p.ksum = ksum;
   p.l = int(l);
   p.h = int(h);
+  p.hd = int(d);
+  p.feature = feature;
   p.tiles = int(cdiv64(l, kRowsPerTile));
-  int splits = sm_count() / int(b * h);
+  int splits = sm_count() / int(b * units);
   if (splits < 1) splits = 1;
   if (splits > p.tiles) splits = p.tiles;
   p.splits = splits;
-  dim3 grid(static_cast<unsigned>(h), splits, static_cast<unsigned>(b));
+  dim3 grid(static_cast<unsigned>(units), splits, static_cast<unsigned>(b));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
 #define TDB_MOM(T)                                                                                                  \
   do {                                                                                                              \
@@ -238,4 +290,14 @@ extern "C" int tdb200_sla_linear_moments(const void* k, const void* v, int dtype
   if (dtype == TDB200_DTYPE_FP16) TDB_MOM(__half);
 #undef TDB_MOM
   return fail(TDB200_ERR_UNSUPPORTED, "sla_linear_moments: dtype tag %d", dtype);
+}
+
+extern "C" int tdb200_sla_linear_moments(const void* k, const void* v, int dtype, int64_t b, int64_t l, int64_t h,
+                                         int64_t d, float* kv, float* ksum, void* stream) {
+  return moments_impl(k, v, dtype, b, l, h, d, 0, kv, ksum, stream);
+}
+
+extern "C" int tdb200_sla_linear_moments_ex(const void* k, const void* v, int dtype, int64_t b, int64_t l, int64_t h,
+                                            int64_t d, int feature, float* kv, float* ksum, void* stream) {
+  return moments_impl(k, v, dtype, b, l, h, d, feature, kv, ksum, stream);
 }
