@@ -57,6 +57,10 @@ const char* tdb200_last_error(void);
  *   k must be a multiple of 8.  x and q 16-byte aligned.
  * ------------------------------------------------------------------------------------------- */
 int tdb200_quant_int8_block128(const void* x, int x_dtype, int64_t m, int64_t k, int8_t* q, float* s, void* stream);
+/* (q, s) = quant_int8_block128( T( gelu_tanh(x) ) ): the FFN activation (nn.GELU(approximate="tanh"),
+ * rcm/networks/wan2pt1.py:375) and the quantisation of the down-projection's input in one HBM pass (2 B read, 1 B written
+ * per element).  gelu in fp32 with one rounding to T, like torch on a 16-bit tensor. */
+int tdb200_gelu_quant_int8_block128(const void* x, int x_dtype, int64_t m, int64_t k, int8_t* q, float* s, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * a2. W8A8 GEMM with per-128-K-block rescale   (ops/gemm/kernel.hpp:391-427, utils.hpp:116-121)
@@ -170,6 +174,12 @@ int tdb200_sla_attn_fwd(const int8_t* q_i8, const float* q_scale, const int8_t* 
                         const void* v, const void* q, int dtype, const int32_t* lut, int64_t topk, const void* kvw,
                         const float* ksum, const float* proj_b, void* out, int64_t b, int64_t l, int64_t lk,
                         int64_t h, int64_t d, float sm_scale, void* stream);
+/* The non-quantised SLA path (reference: Triton _attn_fwd, turbodiffusion/SLA/kernel.py:33-82, used by SparseLinearAttention
+ * when --attention_type sla): the same fused kernel with Q.K^T as a 16-bit tensor-core product on the un-quantised q, k
+ * [b,l,h,d] (fp32 scores, exp2 softmax, P rounded to T before P.V, :60-73); no q/k scales, no key smoothing. */
+int tdb200_sla_attn_fwd_qk16(const void* q, const void* k, const void* v, int dtype, const int32_t* lut, int64_t topk,
+                             const void* kvw, const float* ksum, const float* proj_b, void* out, int64_t b, int64_t l,
+                             int64_t lk, int64_t h, int64_t d, float sm_scale, void* stream);
 /* Second-generation fused kernel (persistent tiles, two softmax threads per query row, linear branch folded into the
  * P.V accumulator); same arguments plus `feature`: 0 softmax, 1 elu+1, 2 relu feature map of the linear branch
  * (SLA/core.py:57-73; the moments must have been built with the same map). */

@@ -91,7 +91,11 @@ def test_argument_validation_of_every_kernel_family(libpath):
         ("sla prep head dim", lambda: lib.tdb200_sla_quant_qk(_p(), _p(), 0, 1, 256, 256, 2, 96, _p(), _p(), _p(), _p(), _p(), _p(), _p(), None),
          UNSUPPORTED, b"head dim"),
         ("block map topk", lambda: lib.tdb200_sla_block_map(_p(), _p(), 0, 1, 2, 4, 8, 128, 9, _p(), _p(), None), INVALID, b"topk"),
-        ("moments head dim", lambda: lib.tdb200_sla_linear_moments(_p(), _p(), 0, 1, 256, 2, 64, _p(), _p(), None), UNSUPPORTED, b"head dim"),
+        ("moments head dim", lambda: lib.tdb200_sla_linear_moments(_p(), _p(), 0, 1, 256, 2, 96, _p(), _p(), None), UNSUPPORTED, b"head dim"),
+        ("moments feature map", lambda: lib.tdb200_sla_linear_moments_ex(_p(), _p(), 0, 1, 256, 2, 64, 7, _p(), _p(), None), INVALID, b"feature"),
+        ("attn v2 head dim", lambda: lib.tdb200_sla_attn_fwd_v2(_p(), _p(), _p(), _p(), _p(), _p(), 0, _p(), 4, _p(), _p(), _p(), _p(), 1, 256,
+                                                                256, 2, 96, 0.088, 0, None), UNSUPPORTED, b"head dim"),
+        ("gelu quant k", lambda: lib.tdb200_gelu_quant_int8_block128(_p(), 0, 128, 100, _p(), _p(), None), UNSUPPORTED, b"multiple of 8"),
         ("attn null", lambda: lib.tdb200_sla_attn_fwd(None, _p(), _p(), _p(), _p(), _p(), 0, _p(), 4, _p(), _p(), _p(), _p(), 1, 256, 256, 2,
                                                       128, 0.088, None), INVALID, b"null"),
         ("attn topk", lambda: lib.tdb200_sla_attn_fwd(_p(), _p(), _p(), _p(), _p(), _p(), 0, _p(), 9, _p(), _p(), _p(), _p(), 1, 256, 256, 2,

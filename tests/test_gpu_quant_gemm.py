@@ -162,10 +162,11 @@ def test_gemm_with_fused_quantised_output_is_bit_exact(cuda, m, n, k, gelu):
 @pytest.mark.parametrize("m,n,k", [(300, 512, 256), (1000, 1280, 384)])
 def test_gelu_epilogue_vs_oracle_gelu(cuda, m, n, k):
     """The fused GELU(tanh) epilogue against the ORACLE's GELU (torch's fp32 tanh on the bf16 pre-activation, the value
-    nn.GELU(approximate="tanh") produces for a bf16 tensor, rcm/networks/wan2pt1.py:375).  The kernel evaluates tanh with
-    MUFU (tanh.approx, |rel err| <= 2^-11): every output is within ONE bf16 ulp of the oracle, more than 99 % are
-    bit-identical; the int8 codes of the fused quantised output differ by at most one code on a small fraction of the
-    elements and the block scales are within one bf16 ulp of the oracle's (the scale is amax/128 of bf16 values)."""
+    nn.GELU(approximate="tanh") produces for a bf16 tensor, rcm/networks/wan2pt1.py:375).  The 16-bit epilogue evaluates
+    x * sigmoid(2u): every output is within ONE bf16 ulp of the oracle (or 1e-6 absolute in the cancelling negative tail),
+    more than 99 % of the non-tiny values are bit-identical.  The quantised-output epilogue uses the one-MUFU tanh: its int8
+    codes differ by at most one code on a small fraction of the elements and the block scales are within one bf16 ulp of
+    the oracle's (the scale is amax/128 of bf16 values).  The one-pass gelu_quant kernel is held to the same bound."""
     import torch.nn.functional as F
     from turbodiffusion_b200.turbo_diffusion_ops import gemm_cuda_bias_gelu, gemm_cuda_quant_out
     x = _mk(m, k, 31 * m + k)
@@ -179,15 +180,26 @@ def test_gelu_epilogue_vs_oracle_gelu(cuda, m, n, k):
     pre = O.int8_gemm(a_q, a_s, b_q, b_s, torch.bfloat16, bias)           # bit-exact pre-activation (tested above)
     ref = F.gelu(pre, approximate="tanh")                                   # bf16 in, fp32 opmath, bf16 out
     got = c.cpu()
-    ulp = (got.view(torch.int16).to(torch.int32) - ref.view(torch.int16).to(torch.int32)).abs()
-    # values that straddle zero compare by magnitude instead of by bit pattern
-    tiny = (got.float().abs() < 1e-30) | (ref.float().abs() < 1e-30) | (got.float().sign() != ref.float().sign())
-    ok = (ulp <= 1) | (tiny & ((got.float() - ref.float()).abs() <= 1e-6))
-    assert ok.all(), (ulp[~ok].max().item(), (~ok).sum().item())
-    assert (ulp[~tiny] == 0).float().mean().item() > 0.99
+    # torch evaluates 0.5 x (1 + tanh(u)) in fp32: in the negative tail 1 + tanh(u) cancels and torch's own result is only
+    # good to ~1e-7 absolute; the kernel evaluates x * sigmoid(2u) (no cancellation).  So: one ulp of T, or 1e-6 absolute.
+    diff = (got.float() - ref.float()).abs()
+    ok = diff <= torch.maximum(2.0 ** -8 * ref.float().abs(), torch.tensor(1e-6))
+    assert ok.all(), (diff[~ok].max().item(), (~ok).sum().item())
+    big = ref.float().abs() > 1e-3
+    same = got.view(torch.int16)[big] == ref.view(torch.int16)[big]
+    assert same.float().mean().item() > 0.99
     q, s = gemm_cuda_quant_out(*dev, torch.bfloat16, gelu=True)
     q_ref, s_ref = O.int8_quant(ref)
     torch.cuda.synchronize()
     assert ((s.cpu() - s_ref).abs() <= 2.0 ** -7 * s_ref).all()
     dq = (q.cpu().to(torch.int16) - q_ref.to(torch.int16)).abs()
     assert dq.max().item() <= 1 and (dq > 0).float().mean().item() < 2e-2, (dq.max().item(), (dq > 0).float().mean().item())
+    # the split path: T(acc + bias) from the GEMM, then GELU + quantisation in one pass
+    from turbodiffusion_b200.turbo_diffusion_ops import gelu_quant_cuda, gemm_cuda_swizzle_bias
+    c2 = torch.empty(m, n, dtype=torch.bfloat16, device=cuda)
+    gemm_cuda_swizzle_bias(dev[0], dev[1], dev[2], dev[3], c2, dev[4])
+    assert torch.equal(c2.cpu().view(torch.int16), pre.view(torch.int16))
+    q3, s3 = gelu_quant_cuda(c2)
+    dq3 = (q3.cpu().to(torch.int16) - q_ref.to(torch.int16)).abs()
+    assert dq3.max().item() <= 1 and (dq3 > 0).float().mean().item() < 2e-3, (dq3.max().item(), (dq3 > 0).float().mean().item())
+    assert ((s3.cpu() - s_ref).abs() <= 2.0 ** -7 * s_ref).all()

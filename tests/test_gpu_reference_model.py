@@ -52,8 +52,11 @@ def _build(mm, dim, heads, ffn, layers, text_len, attention, topk):
                 nrm.weight.normal_(1.0, 0.1)
             blk.norm3.weight.normal_(1.0, 0.1)
             blk.norm3.bias.normal_(0, 0.05)
-    m = m.to("cuda").to(torch.bfloat16)
+    # the reference flow (modify_model.py:159-183): bf16 checkpoint weights, replace_attention (fp32 proj_l), move to the GPU,
+    # then replace_linear_norm, which quantises the linears on the device
+    m = m.to(torch.bfloat16)
     mm.replace_attention(m, attention, topk)
+    m = m.to("cuda")
     mm.replace_linear_norm(m, replace_linear=True, replace_norm=True, quantize=True)
     with torch.no_grad():
         for blk in m.blocks:  # proj_l is zero-initialised (SLA/core.py:163-166): give the linear branch something to do
@@ -95,7 +98,7 @@ def test_reference_wan_model_forward_on_b200_operators(cuda, attention):
 
     for i, (xin, kw, out) in enumerate(captured):
         sd = {k: v for k, v in m.blocks[i].state_dict().items()}
-        blk = WanBlockB200(sd, dim, heads, eps=1e-6, topk=topk)
+        blk = WanBlockB200(sd, dim, heads, eps=1e-6, topk=topk, attention=attention)
         got = blk(xin[0], kw["e"][0].float(), kw["freqs"].view(xin.shape[1], -1).float(), kw["context"][0])
         s = O.stats(got.cpu(), out[0].cpu())
         assert s["cos"] >= 0.9999 and s["rel_l2"] <= 1e-2, (attention, i, s)

@@ -175,7 +175,38 @@ def test_sla_forward_vs_reference_golden(cuda, name):
         mod.proj_l.bias.copy_(g["proj_b"])
     out = mod(g["q"].to(cuda), g["k"].to(cuda), g["v"].to(cuda)).cpu()
     s = O.stats(out, g["out"])
-    assert s["cos"] >= 0.999 and s["rel_l2"] <= 2e-2, s
+    # 128-wide heads: the 16-bit-QK kernel against the reference's Triton path (rel-L2 <= 5e-3 for the bf16 path)
+    assert s["cos"] >= 0.9999 and s["rel_l2"] <= 5e-3, s
+    # the Sage (INT8-QK) module on the same inputs stays inside its own, wider bound
+    from turbodiffusion_b200.SLA import SageSparseLinearAttention
+    sage = SageSparseLinearAttention(d, g["topk_ratio"]).to(cuda)
+    sage.load_state_dict(mod.state_dict())
+    s2 = O.stats(sage(g["q"].to(cuda), g["k"].to(cuda), g["v"].to(cuda)).cpu(), g["out"])
+    assert s2["cos"] >= 0.999 and s2["rel_l2"] <= 2e-2, s2
+    assert s["rel_l2"] < s2["rel_l2"]
+
+
+@pytest.mark.parametrize("b,l,h,ratio", [(1, 600, 2, 0.25), (2, 333, 3, 0.5), (1, 1280, 2, 0.1), (1, 700, 1, 1.0)])
+def test_sla_16bit_qk_forward_vs_oracle(cuda, b, l, h, ratio):
+    """SparseLinearAttention (a9'): against the oracle's restatement of the Triton path (P rounded to T, SLA/kernel.py:73) and
+    the fp32 oracle, on the kernel's own block selection; ragged tails and the dense case included."""
+    from turbodiffusion_b200.SLA import SparseLinearAttention
+    d = 128
+    q, k, v = _qkv(b, l, h, d, 2000 + l)
+    g = torch.Generator().manual_seed(5)
+    mod = SparseLinearAttention(d, ratio, BLKQ=128, BLKK=64).to(cuda)
+    with torch.no_grad():
+        mod.proj_l.weight.copy_(torch.randn(d, d, generator=g) * 0.05)
+        mod.proj_l.bias.copy_(torch.randn(d, generator=g) * 0.05)
+    out, sel = mod.forward_with_lut(q.to(cuda), k.to(cuda), v.to(cuda))
+    torch.cuda.synchronize()
+    lut = sel["lut"].cpu()
+    w, bias = mod.proj_l.weight.detach().cpu(), mod.proj_l.bias.detach().cpu()
+    exact = O.sla_forward(q, k, v, w, bias, ratio, mode="exact", lut=lut)
+    tri = O.sla_forward(q, k, v, w, bias, ratio, mode="triton", lut=lut)
+    s_exact, s_tri = O.stats(out.cpu(), exact), O.stats(out.cpu(), tri)
+    assert s_exact["cos"] >= 0.9999 and s_exact["rel_l2"] <= 5e-3, (s_exact, s_tri)
+    assert s_tri["rel_l2"] <= 5e-3, (s_exact, s_tri)
 
 
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
@@ -283,3 +314,93 @@ def test_sage_sla_forward_large_scores_exercise_the_lazy_rescale(cuda, pattern, 
     s_sage, s_exact = O.stats(out.cpu(), sage), O.stats(out.cpu(), exact)
     assert s_sage["rel_l2"] <= 3e-2, (s_sage, s_exact)       # the emulation itself is 4-5e-2 away from fp32 on these inputs
     assert s_exact["cos"] >= 0.99, (s_sage, s_exact)
+
+
+@pytest.mark.parametrize("feature_map,d,l,h,ratio", [("elu", 128, 600, 2, 0.25), ("relu", 128, 333, 3, 0.5), ("softmax", 64, 1000, 3, 0.15),
+                                                     ("elu", 64, 700, 2, 0.3)])
+def test_sla_feature_maps_and_native_64_wide_heads(cuda, feature_map, d, l, h, ratio):
+    """SLA/core.py:57-73 feature maps (elu+1, relu) of the linear branch and 64-wide heads (SLA/core.py:207) on the native
+    tiles (odd head counts exercise the unpaired head of the moments kernel).  Oracle: fp32 block-sparse attention + fp32
+    linear branch with the same feature map on the kernel's own block selection."""
+    from turbodiffusion_b200.SLA import SageSparseLinearAttention
+    q, k, v = _qkv(1, l, h, d, 6000 + l + d)
+    q = (q.float() * 0.5).bfloat16()          # keep elu/relu features in a range where the linear branch matters
+    g = torch.Generator().manual_seed(8)
+    mod = SageSparseLinearAttention(d, ratio, feature_map=feature_map).to(cuda)
+    with torch.no_grad():
+        mod.proj_l.weight.copy_(torch.randn(d, d, generator=g) * 0.05)
+        mod.proj_l.bias.copy_(torch.randn(d, generator=g) * 0.05)
+    out, sel = mod.forward_with_lut(q.to(cuda), k.to(cuda), v.to(cuda))
+    torch.cuda.synchronize()
+    lut = sel["lut"].cpu()
+    w, b = mod.proj_l.weight.detach().cpu(), mod.proj_l.bias.detach().cpu()
+    mblk = (l + 127) // 128
+    worst = 0.0
+    for head in range(h):
+        for m in range(mblk):
+            ref = O.sla_forward_block(q, k, v, w, b, head, m, lut[0, head, m], mode="exact", feature_map=feature_map)
+            got = out[0, m * 128:min(l, (m + 1) * 128), head].cpu()
+            s = O.stats(got, ref)
+            assert s["cos"] >= 0.999 and s["rel_l2"] <= 2e-2, (feature_map, d, head, m, s)
+            worst = max(worst, s["rel_l2"])
+    print("feature map", feature_map, d, "worst rel_l2", worst)
+
+
+@pytest.mark.parametrize("d,h,feature", [(64, 3, 0), (64, 4, 1), (128, 2, 2)])
+def test_linear_moments_head_dims_and_feature_maps(cuda, d, h, feature):
+    from turbodiffusion_b200.SLA.core import linear_moments
+    l = 700
+    _, k, v = _qkv(1, l, h, d, 90 + d + h)
+    kv, ksum = linear_moments(k.to(cuda), v.to(cuda), feature)
+    torch.cuda.synchronize()
+    fq, fk = O.feature_maps(["softmax", "elu", "relu"][feature])
+    kh, vh = k.transpose(1, 2).float(), v.transpose(1, 2).float()
+    phi = fk(kh).to(k.dtype).float()
+    kv_ref = vh.transpose(-1, -2) @ phi
+    s_kv, s_ks = O.stats(kv.cpu(), kv_ref), O.stats(ksum.cpu(), phi.sum(-2))
+    assert s_kv["rel_l2"] < 3e-3 and s_ks["rel_l2"] < 3e-3, (s_kv, s_ks)
+
+
+def test_ltx_sparse_only_call_sequence(cuda):
+    """The call sequence of TurboT2AV's LTXSageSLAAttention._sparse_only_forward (ltx_distillation/acceleration.py:260-383)
+    against the names it looks up in SLA.core; with proj_l == 0 it must equal SageSparseLinearAttention.forward."""
+    import turbodiffusion_b200.SLA.core as sla_core
+    from turbodiffusion_b200.SLA import SageSparseLinearAttention
+    b, l, h, d, topk = 1, 900, 2, 128, 0.3
+    q, k, v = (t.to(cuda) for t in _qkv(b, l, h, d, 321))
+    mod = SageSparseLinearAttention(d, topk).to(cuda)          # proj_l zero-initialised (SLA/core.py:163-166)
+    want = mod(q, k, v)
+    qh, kh, vh = (t.transpose(1, 2).contiguous() for t in (q, k, v))
+    assert sla_core.get_cuda_arch(0) == "sm100"
+    sparse_map, _, _ = sla_core.get_block_map(qh, kh, topk_ratio=topk, BLKQ=128, BLKK=64)
+    km = kh.mean(dim=-2, keepdim=True)
+    q_int8, q_scale, k_int8, k_scale = sla_core.get_vanilla_qk_quant(qh, kh, km, 128, 64)
+    lut, valid_block_num = sla_core.block_map_lut_triton(sparse_map)
+    assert (valid_block_num == int(topk * ((l + 63) // 64))).all()
+    o_s = torch.empty_like(qh)
+    padded = (l + 127) // 128 * 128
+    v_t = torch.empty((b, h, d, padded), dtype=vh.dtype, device=cuda)
+    sla_core.fused.transpose_pad_permute_cuda(vh, v_t, 1)
+    v_fp8 = torch.empty(v_t.shape, dtype=torch.float8_e4m3fn, device=cuda)
+    v_scale = torch.empty((b, h, d), dtype=torch.float32, device=cuda)
+    sla_core.fused.scale_fuse_quant_cuda(v_t, v_fp8, v_scale, l, 2.25, 1)
+    pv = torch.full((h,), 1e6, dtype=torch.float32, device=cuda)
+    assert sla_core.SAGE2PP_ENABLED
+    sla_core.qk_int8_sv_f8_accum_f16_block_sparse_attn_inst_buf_fuse_v_scale_with_pv_threshold(
+        q_int8, k_int8, v_fp8, o_s, lut, valid_block_num, pv, q_scale, k_scale, v_scale, 1, False, 1, 1.0 / d ** 0.5, 0)
+    got = o_s.transpose(1, 2)
+    assert torch.equal(got.contiguous(), want)
+    # a map that did not come from get_block_map is rebuilt from its entries
+    lut2, _ = sla_core.block_map_lut_triton(sparse_map.clone())
+    assert torch.equal(lut2, lut)
+    with pytest.raises(NotImplementedError):
+        sla_core.qattn.qk_int8_sv_f16_accum_f16_block_sparse_attn_inst_buf_with_pv_threshold
+
+
+def test_mean_pool_block_sizes(cuda):
+    from turbodiffusion_b200.SLA.utils import mean_pool
+    x = _qkv(1, 700, 2, 128, 55)[1].transpose(1, 2).contiguous()
+    for blk in (64, 128):
+        got = mean_pool(x.to(cuda), blk).cpu()
+        ref = O.mean_pool(x, blk)
+        assert (got.float() - ref.float()).abs().max() <= 2.0 ** -6 * ref.float().abs().max()

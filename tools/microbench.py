@@ -57,6 +57,10 @@ def main():
     args = ap.parse_args()
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
     results = []
+    filters = [f for f in args.filter.split(",") if f] or [""]
+
+    def match(name):
+        return any(f in name for f in filters)
 
     def record(name, ms_med, ms_min, flops=None, bytes_=None, **extra):
         r = {"name": name, "ms_median": round(ms_med, 4), "ms_min": round(ms_min, 4)}
@@ -75,7 +79,7 @@ def main():
         gemms = [("qkv_fused", L, 3 * dim, dim), ("o_proj", L, dim, dim), ("ffn_up", L, ffn, dim), ("ffn_down", L, dim, ffn)]
         for name, m, n, k in gemms:
             full = f"gemm_w8a8/{tag}/{name}/{m}x{n}x{k}"
-            if args.filter not in full:
+            if not match(full):
                 continue
             a = torch.randint(-128, 128, (m, k), device=dev, dtype=torch.int8)
             b = torch.randint(-128, 128, (n, k), device=dev, dtype=torch.int8)
@@ -94,13 +98,19 @@ def main():
             del a, b, c
         for name, k in (("dim", dim), ("ffn", ffn)):
             full = f"quant_int8/{tag}/{name}/{L}x{k}"
-            if args.filter in full:
+            if match(full):
                 x = torch.randn(L, k, device=dev, dtype=torch.bfloat16)
                 q = torch.empty(L, k, dtype=torch.int8, device=dev)
                 s = torch.empty((L + 127) // 128, k // 128, device=dev)
                 med, mn = timeit(lambda: tdo.quant_cuda(x, q, s), args.iters)
                 record(full, med, mn, bytes_=3 * L * k)
                 del x, q
+        full = f"gelu_quant_int8/{tag}/ffn/{L}x{ffn}"
+        if match(full):
+            xg = torch.randn(L, ffn, device=dev, dtype=torch.bfloat16)
+            med, mn = timeit(lambda: tdo.gelu_quant_cuda(xg), args.iters)
+            record(full, med, mn, bytes_=3 * L * ffn)
+            del xg
         x = torch.randn(L, dim, device=dev, dtype=torch.bfloat16)
         w = torch.rand(dim, device=dev) + 0.5
         sc, sh = torch.randn(dim, device=dev) * 0.1, torch.randn(dim, device=dev) * 0.1
@@ -115,7 +125,7 @@ def main():
         ang = torch.rand(L, 64, device=dev) * 20
         rows.append((f"rmsnorm_rope/{tag}/{L}x{dim}", lambda: ops.rmsnorm_rope(x, w, ang, 1e-6, heads), 4 * L * dim))
         for full, fn, nbytes in rows:
-            if args.filter in full:
+            if match(full):
                 med, mn = timeit(fn, args.iters)
                 record(full, med, mn, bytes_=nbytes)
         del x
@@ -124,7 +134,7 @@ def main():
     from turbodiffusion_b200 import ltx
     for name, m, n, k in [("ltx_proj", 28672, 4096, 4096), ("ltx_ffn_up", 28672, 16384, 4096), ("ltx_ffn_down", 28672, 4096, 16384)]:
         full = f"gemm_w8a8_rowwise/C/{name}/{m}x{n}x{k}"
-        if args.filter not in full:
+        if not match(full):
             continue
         a = torch.randint(-128, 128, (m, k), device=dev, dtype=torch.int8)
         b = torch.randint(-128, 128, (n, k), device=dev, dtype=torch.int8)
@@ -144,7 +154,7 @@ def main():
                  ("C", 28672, 32, 128, (0.3,))]
     for tag, L, H, D, ratios in sla_cases:
         prefixes = [f"sla_{part}/{tag}/" for part in ("prep", "block_map", "moments", "attn", "module")]
-        if args.filter and not any(args.filter in n or args.filter.startswith(n) for n in prefixes):
+        if args.filter and not any(f in n or f.startswith(n) for n in prefixes for f in filters):
             continue  # (a selected case runs all of its parts: they share the prepared tensors)
         g = torch.Generator(device="cuda").manual_seed(0)
         q = torch.randn(1, L, H, D, device=dev, generator=g).bfloat16()

@@ -92,10 +92,12 @@ def mean_pool(x: torch.Tensor, BLK: int) -> torch.Tensor:
     """SLA/utils.py:44-52 for x [B, H, L, D]; BLK in {64, 128}.  (Uses the fused prepass on a [B,L,H,D] view.)"""
     assert x.is_contiguous() and BLK in (64, 128)
     xt = x.transpose(1, 2).contiguous()
-    prep = quant_qk(xt, xt)
     if BLK == 128:
-        return prep.q_pool
-    raise NotImplementedError("mean_pool(BLK=64) of un-smoothed keys is not part of the hot path; use quant_qk")
+        return quant_q_only(xt).q_pool
+    # 64-row blocks: the key half of the prepass pools (k - mean_L k); adding the T-rounded mean back gives the plain
+    # block means up to one rounding of T (the reference pools the tensor it is handed, SLA/utils.py:44-52)
+    prep = quant_k_into(QKPrep(), xt, xt.shape[1])
+    return (prep.k_pool.float() + prep.kmean.to(x.dtype).float()[:, :, None, :]).to(x.dtype)
 
 
 def get_block_map(q: torch.Tensor, k: torch.Tensor, topk_ratio: float, BLKQ: int = 128, BLKK: int = 64):
@@ -107,4 +109,5 @@ def get_block_map(q: torch.Tensor, k: torch.Tensor, topk_ratio: float, BLKQ: int
     nblk = prep.nblk
     topk = min(nblk, int(topk_ratio * nblk))
     sparse_map, lut = block_map_from_pools(prep.q_pool, prep.k_pool, topk)
+    sparse_map._tdb200_lut = lut   # SLA.core.block_map_lut_triton hands this back instead of rebuilding it from the map
     return sparse_map, lut, topk

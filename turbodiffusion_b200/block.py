@@ -12,14 +12,23 @@ Weights use the reference's checkpoint format (Int8Linear buffers `int8_weight`,
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, Optional
 
 import torch
 import torch.nn.functional as F
 
 from . import ops
-from .SLA.core import SageSparseLinearAttention
-from .turbo_diffusion_ops import gemm_cuda_bias_gelu, gemm_cuda_quant_out, gemm_cuda_swizzle_bias, quant_cuda
+from .SLA.core import SageSparseLinearAttention, SparseLinearAttention
+from .turbo_diffusion_ops import (gelu_quant_cuda, gemm_cuda_bias_gelu, gemm_cuda_quant_out, gemm_cuda_swizzle_bias,
+                                  quant_cuda)
+
+# FFN activation between the two W8A8 GEMMs:
+#   "split": up-projection writes T(acc + bias); one HBM pass applies GELU(tanh) and the 128x128-block quantisation
+#            (tdb200_gelu_quant_int8_block128): exact fp32 GELU, and the GEMM's dequant warps do not carry the activation;
+#   "fused": bias + GELU (one-MUFU tanh) + quantisation in the up-projection's epilogue: no 16-bit intermediate in HBM, but
+#            the epilogue runs on the warps that dequantise (measured: 0.886 ms vs 0.552 ms for the plain GEMM at shape A).
+FFN_ACT_MODE = os.environ.get("TDB200_FFN_ACT", "split")
 
 LINEARS = ("self_attn.q", "self_attn.k", "self_attn.v", "self_attn.o", "cross_attn.q", "cross_attn.k", "cross_attn.v",
            "cross_attn.o", "ffn.0", "ffn.2")
@@ -53,7 +62,8 @@ def random_block_state(dim: int, ffn_dim: int, heads: int, seed: int, device, dt
 class WanBlockB200:
     """One DiT block on the B200 operators.  `sd` uses the reference state-dict keys relative to `blocks.<i>.`."""
 
-    def __init__(self, sd: Dict[str, torch.Tensor], dim: int, heads: int, eps: float = 1e-6, topk: float = 0.1):
+    def __init__(self, sd: Dict[str, torch.Tensor], dim: int, heads: int, eps: float = 1e-6, topk: float = 0.1,
+                 attention: str = "sagesla"):
         # norm weights / modulation are read by the fused kernels through fp32 pointers: a checkpoint loaded with
         # load_state_dict(assign=True) may hold them in bf16, so normalise them ONCE here (no per-call casts)
         sd = dict(sd)
@@ -64,7 +74,9 @@ class WanBlockB200:
         self.sd, self.dim, self.heads, self.eps = sd, dim, heads, eps
         self.head_dim = dim // heads
         dev = sd["modulation"].device
-        self.sla = SageSparseLinearAttention(self.head_dim, topk).to(dev)
+        # modify_model.py:48-52: "sagesla" -> SageSparseLinearAttention (INT8 Q.K^T), "sla" -> SparseLinearAttention(BLKQ=128, BLKK=64)
+        self.sla = (SageSparseLinearAttention(self.head_dim, topk) if attention == "sagesla"
+                    else SparseLinearAttention(self.head_dim, topk, BLKQ=128, BLKK=64)).to(dev)
         with torch.no_grad():
             self.sla.proj_l.weight.copy_(sd["self_attn.attn_op.local_attn.proj_l.weight"])
             self.sla.proj_l.bias.copy_(sd["self_attn.attn_op.local_attn.proj_l.bias"])
@@ -134,7 +146,10 @@ class WanBlockB200:
         # ---- FFN (:411-413)
         hq, hs = ops.layernorm_modulate_quant_from_stats(x, st2, e[4], e[3])
         # Linear -> GELU(tanh) -> quant for the down projection, all in the up-projection's epilogue
-        uq, us = gemm_cuda_quant_out(hq, hs, sd["ffn.0.int8_weight"], sd["ffn.0.scale"], sd["ffn.0.bias"], x.dtype, gelu=True)
+        if FFN_ACT_MODE == "fused":
+            uq, us = gemm_cuda_quant_out(hq, hs, sd["ffn.0.int8_weight"], sd["ffn.0.scale"], sd["ffn.0.bias"], x.dtype, gelu=True)
+        else:
+            uq, us = gelu_quant_cuda(self._gemm(hq, hs, "ffn.0", x.dtype))
         y = self._gemm(uq, us, "ffn.2", x.dtype)
         if want_stats:
             return ops.gate_residual_stats(x, y, e[5], eps)

@@ -373,6 +373,11 @@ struct F16Traits<__nv_bfloat16> {
     return *reinterpret_cast<uint32_t*>(&v);
   }
   static __device__ __forceinline__ float round(float a) { return __bfloat162float(__float2bfloat16_rn(a)); }
+  // packed a + b with ONE rounding per lane: exactly what a bf16 tensor add produces
+  static __device__ __forceinline__ uint32_t add2(uint32_t a, uint32_t b) {
+    __nv_bfloat162 r = __hadd2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
+    return *reinterpret_cast<uint32_t*>(&r);
+  }
 };
 template <>
 struct F16Traits<__half> {
@@ -387,6 +392,10 @@ struct F16Traits<__half> {
     return *reinterpret_cast<uint32_t*>(&v);
   }
   static __device__ __forceinline__ float round(float a) { return __half2float(__float2half_rn(a)); }
+  static __device__ __forceinline__ uint32_t add2(uint32_t a, uint32_t b) {
+    __half2 r = __hadd2(*reinterpret_cast<__half2*>(&a), *reinterpret_cast<__half2*>(&b));
+    return *reinterpret_cast<uint32_t*>(&r);
+  }
 };
 
 // bare MUFU.EX2 (no denormal fix-up code around it)

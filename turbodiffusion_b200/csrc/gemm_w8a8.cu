@@ -31,7 +31,7 @@
 #define TDB_GEMM_STAGES 3    // TMA ring depth: 3 (8 KB staging per warp, one store round) or 4 (4 KB staging, two rounds)
 #endif
 #ifndef TDB_GEMM_XPF
-#define TDB_GEMM_XPF 2       // request chunk 0 of K-block kb+1 before converting the last chunk of kb: 0 never, 1 always (may block), 2 when its MMAs are done
+#define TDB_GEMM_XPF 0       // request chunk 0 of K-block kb+1 before converting the last chunk of kb: 0 never (fastest), 1 always (may block), 2 when its MMAs are done
 #endif
 
 namespace {
@@ -434,16 +434,11 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          float y0 = acc[ch * 8 + 2 * j], y1 = acc[ch * 8 + 2 * j + 1];
-          if (bias != nullptr) {
-            y0 = F16Traits<T>::round(y0) + F16Traits<T>::lo(bw[j]);
-            y1 = F16Traits<T>::round(y1) + F16Traits<T>::hi(bw[j]);
-          }
-          if (act_gelu) {
-            y0 = gelu_precise(F16Traits<T>::round(y0));
-            y1 = gelu_precise(F16Traits<T>::round(y1));
-          }
-          w[j] = F16Traits<T>::pack(y0, y1);
+          // T(acc) then the packed 16-bit add: one rounding each, exactly the module's `out + bias` on 16-bit tensors
+          uint32_t y = F16Traits<T>::pack(acc[ch * 8 + 2 * j], acc[ch * 8 + 2 * j + 1]);
+          if (bias != nullptr) y = F16Traits<T>::add2(y, bw[j]);
+          if (act_gelu) y = F16Traits<T>::pack(gelu_precise(F16Traits<T>::lo(y)), gelu_precise(F16Traits<T>::hi(y)));
+          w[j] = y;
         }
         *reinterpret_cast<uint4*>(stage + (kStoreRounds == 2 ? 0 : (ch >> 3) * 4096) + lane * 128 + (((ch & 7) ^ (lane & 7)) << 4)) =
             make_uint4(w[0], w[1], w[2], w[3]);

@@ -265,14 +265,13 @@ int launch_rows(const RowParams& p, cudaStream_t st) {
 #define TDB_LAUNCH_W(CH)                                                                   \
   row_norm_kernel<T, kNorm, kPost, 256, CH, kResidIn, true><<<wgrid, 256, 0, st>>>(p);    \
   return check_launch("row_norm_kernel(warp)")
+    // measured (profiles/r02_microbench_prologue.jsonl): the warp-per-row form wins for dim 1536 (LayerNorm 0.61 -> 0.79 of the HBM
+    // peak, RMSNorm+RoPE 0.37 -> 0.49) and loses for dim 5120 (20 chunks per lane: registers cut the occupancy), so it is
+    // used up to 8 chunks per lane (n <= 2048 16-bit elements)
     if (nchunks <= 32 * 2) { TDB_LAUNCH_W(2); }
     if (nchunks <= 32 * 4) { TDB_LAUNCH_W(4); }
     if (nchunks <= 32 * 6) { TDB_LAUNCH_W(6); }
     if (nchunks <= 32 * 8) { TDB_LAUNCH_W(8); }
-    if (nchunks <= 32 * 12) { TDB_LAUNCH_W(12); }
-    if (nchunks <= 32 * 16) { TDB_LAUNCH_W(16); }
-    if (nchunks <= 32 * 20) { TDB_LAUNCH_W(20); }
-    if (nchunks <= 32 * 24) { TDB_LAUNCH_W(24); }
 #undef TDB_LAUNCH_W
   }
   const unsigned grid = static_cast<unsigned>(p.m);

@@ -16,7 +16,24 @@ constexpr int kThreads = 256;
 constexpr int kRowsPerPass = kThreads / 16;      // 16 rows per pass (16 lanes x 16 B cover one 256-byte row segment)
 constexpr int kPasses = kBlk / kRowsPerPass;     // 8
 
-template <typename T>
+// kGelu: the input is the FFN's pre-activation; y = T(gelu_tanh(x)) (nn.GELU(approximate="tanh") on a 16-bit tensor: fp32
+// math, one rounding, rcm/networks/wan2pt1.py:375) is quantised instead of x.  gelu_tanh(x) = x * sigmoid(2u),
+// u = sqrt(2/pi)(x + 0.044715 x^3), evaluated as x / (1 + 2^z) with ex2.approx + rcp.approx (relative error ~2^-21 everywhere,
+// including the negative tail where 1 + tanh(u) cancels).
+// sigmoid(2u(x)) = 1 / (1 + 2^z), z = -2 log2(e) sqrt(2/pi) (x + 0.044715 x^3).  One MUFU (ex2); the reciprocal runs on the FMA pipe
+// (integer-trick seed + three Newton steps, relative error < 1e-6), because the XU pipe is what bounds this kernel: with a second
+// MUFU per element it ran at 0.47 of the HBM peak (profiles/r02_microbench_prologue.jsonl).
+__device__ __forceinline__ float sigmoid_2u(float x) {
+  const float z = fminf(x * fmaf(-0.10294324f, x * x, -2.3022082f), 120.0f);
+  const float d = 1.0f + fast_exp2(z);                       // in [1, 2^120]
+  float r = __int_as_float(0x7EF311C7 - __float_as_int(d));   // 1/d within 12 %
+  r = r * fmaf(-d, r, 2.0f);
+  r = r * fmaf(-d, r, 2.0f);
+  r = r * fmaf(-d, r, 2.0f);
+  return r;
+}
+
+template <typename T, bool kGelu = false>
 __global__ void __launch_bounds__(kThreads) quant_int8_block128_kernel(const T* __restrict__ x, int8_t* __restrict__ q,
                                                                        float* __restrict__ s, int64_t m, int64_t k,
                                                                        int k_blocks) {
@@ -42,9 +59,14 @@ __global__ void __launch_bounds__(kThreads) quant_int8_block128_kernel(const T* 
     const uint32_t w[4] = {raw[p].x, raw[p].y, raw[p].z, raw[p].w};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      v[p][2 * j] = F16Traits<T>::lo(w[j]);
-      v[p][2 * j + 1] = F16Traits<T>::hi(w[j]);
-      amax = fmaxf(amax, fmaxf(fabsf(v[p][2 * j]), fabsf(v[p][2 * j + 1])));
+      float a = F16Traits<T>::lo(w[j]), b = F16Traits<T>::hi(w[j]);
+      if (kGelu) {
+        a = F16Traits<T>::round(a * sigmoid_2u(a));
+        b = F16Traits<T>::round(b * sigmoid_2u(b));
+      }
+      v[p][2 * j] = a;
+      v[p][2 * j + 1] = b;
+      amax = fmaxf(amax, fmaxf(fabsf(a), fabsf(b)));
     }
   }
   amax = warp_max(amax);
@@ -75,8 +97,7 @@ __global__ void __launch_bounds__(kThreads) quant_int8_block128_kernel(const T* 
 
 }  // namespace
 
-extern "C" int tdb200_quant_int8_block128(const void* x, int x_dtype, int64_t m, int64_t k, int8_t* q, float* s,
-                                          void* stream) {
+static int quant_impl(const void* x, int x_dtype, int64_t m, int64_t k, int8_t* q, float* s, bool gelu, void* stream) {
   using namespace tdb;
   if (!x || !q || !s) return fail(TDB200_ERR_INVALID_ARG, "quant_int8_block128: null pointer");
   if (m < 0 || k < 0) return fail(TDB200_ERR_INVALID_ARG, "quant_int8_block128: negative size");
@@ -89,13 +110,29 @@ extern "C" int tdb200_quant_int8_block128(const void* x, int x_dtype, int64_t m,
   if (mb > 65535) return fail(TDB200_ERR_UNSUPPORTED, "quant_int8_block128: m too large (%lld)", (long long)m);
   dim3 grid(static_cast<unsigned>(kb), static_cast<unsigned>(mb));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (x_dtype == TDB200_DTYPE_BF16)
+  if (x_dtype == TDB200_DTYPE_BF16 && !gelu)
     quant_int8_block128_kernel<__nv_bfloat16>
         <<<grid, kThreads, 0, st>>>(static_cast<const __nv_bfloat16*>(x), q, s, m, k, static_cast<int>(kb));
-  else if (x_dtype == TDB200_DTYPE_FP16)
+  else if (x_dtype == TDB200_DTYPE_FP16 && !gelu)
     quant_int8_block128_kernel<__half><<<grid, kThreads, 0, st>>>(static_cast<const __half*>(x), q, s, m, k,
                                                                   static_cast<int>(kb));
+  else if (x_dtype == TDB200_DTYPE_BF16)
+    quant_int8_block128_kernel<__nv_bfloat16, true>
+        <<<grid, kThreads, 0, st>>>(static_cast<const __nv_bfloat16*>(x), q, s, m, k, static_cast<int>(kb));
+  else if (x_dtype == TDB200_DTYPE_FP16)
+    quant_int8_block128_kernel<__half, true><<<grid, kThreads, 0, st>>>(static_cast<const __half*>(x), q, s, m, k,
+                                                                        static_cast<int>(kb));
   else
     return fail(TDB200_ERR_UNSUPPORTED, "quant_int8_block128: dtype tag %d (only bf16/fp16, like quant.cu:64-67)", x_dtype);
   return check_launch("quant_int8_block128_kernel");
+}
+
+extern "C" int tdb200_quant_int8_block128(const void* x, int x_dtype, int64_t m, int64_t k, int8_t* q, float* s,
+                                          void* stream) {
+  return quant_impl(x, x_dtype, m, k, q, s, false, stream);
+}
+
+extern "C" int tdb200_gelu_quant_int8_block128(const void* x, int x_dtype, int64_t m, int64_t k, int8_t* q, float* s,
+                                               void* stream) {
+  return quant_impl(x, x_dtype, m, k, q, s, true, stream);
 }

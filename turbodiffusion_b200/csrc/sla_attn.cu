@@ -30,18 +30,24 @@ constexpr int D = 128;
 constexpr int BLKQ = 128, BLKK = 64;
 constexpr int kThreads = 192;
 constexpr int kSoftmaxWarps = 4, kTmaWarp = 4, kMmaWarp = 5;
-constexpr uint32_t kQ8Bytes = BLKQ * D;           // 16 KB
-constexpr uint32_t kK8Bytes = BLKK * D;           // 8 KB
 constexpr uint32_t kVBytes = BLKK * D * 2;        // 16 KB (two 64-column blocks of 8 KB)
 constexpr uint32_t kPBytes = BLKQ * BLKK * 2;     // 16 KB
-constexpr int kStages = 3;                        // K and V rings (separate: K is released after Q.K^T, V after P.V)
-constexpr uint32_t kOffQ8 = 0;
-constexpr uint32_t kOffK8 = kOffQ8 + kQ8Bytes;
-constexpr uint32_t kOffV = kOffK8 + kStages * kK8Bytes;
-constexpr uint32_t kOffP = kOffV + kStages * kVBytes;
-constexpr uint32_t kOffBars = kOffP + kPBytes;      // 104 KB
 constexpr uint32_t kBarBytes = 256;
-constexpr uint32_t kOffLut = kOffBars + kBarBytes;
+// kQK16 = false: Sage path, INT8 Q/K tiles (a9).  kQK16 = true: the non-quantised SLA path (a9', SLA/kernel.py:33-82): Q and K
+// are consumed as 16-bit tiles straight from the module layout [B,L,H,D] (two 64-column K-major chunks each), Q.K^T is a
+// kind::f16 MMA into fp32 scores.  The 16-bit tiles are twice as large, so that variant runs two-stage rings.
+template <bool kQK16>
+struct Lay {
+  static constexpr int kStages = kQK16 ? 2 : 3;     // K and V rings (separate: K is released after Q.K^T, V after P.V)
+  static constexpr uint32_t kQBytes = kQK16 ? BLKQ * D * 2 : BLKQ * D;   // 32 KB | 16 KB
+  static constexpr uint32_t kKBytes = kQK16 ? BLKK * D * 2 : BLKK * D;   // 16 KB |  8 KB
+  static constexpr uint32_t kOffQ = 0;
+  static constexpr uint32_t kOffK = kOffQ + kQBytes;
+  static constexpr uint32_t kOffV = kOffK + kStages * kKBytes;
+  static constexpr uint32_t kOffP = kOffV + kStages * kVBytes;
+  static constexpr uint32_t kOffBars = kOffP + kPBytes;      // 104 KB | 112 KB
+  static constexpr uint32_t kOffLut = kOffBars + kBarBytes;
+};
 constexpr uint32_t kTmemCols = 256;
 constexpr uint32_t kColS = 0, kColO = 128;
 constexpr float kLog2e = 1.4426950408889634f;
@@ -74,11 +80,15 @@ enum Bar {
   kBarPhiFull = 21, kBarOlFull = 22, kNumBars = 23
 };
 
-template <typename T>
+template <typename T, bool kQK16>
 __global__ void __launch_bounds__(kThreads, 2)
 sla_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q8, const __grid_constant__ CUtensorMap tmap_k8,
                     const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_kvw,
                     AttnParams p) {
+  using L = Lay<kQK16>;
+  constexpr int kStages = L::kStages;
+  constexpr uint32_t kOffQ8 = L::kOffQ, kOffK8 = L::kOffK, kOffV = L::kOffV, kOffP = L::kOffP, kOffBars = L::kOffBars, kOffLut = L::kOffLut;
+  constexpr uint32_t kQ8Bytes = L::kQBytes, kK8Bytes = L::kKBytes;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // 1024-aligned, stays a shared-space pointer
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBars);
@@ -118,7 +128,7 @@ sla_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q8, const __grid_co
     for (int i = threadIdx.x; i < T_blocks; i += kThreads) {
       const int blk = __ldg(lut_row + i);
       s_lut[i] = static_cast<uint16_t>(blk);
-      s_ksc[i] = __ldg(ksc_row + blk);
+      s_ksc[i] = kQK16 ? 1.0f : __ldg(ksc_row + blk);
     }
   }
   tc_fence_before_sync();
@@ -134,14 +144,24 @@ sla_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q8, const __grid_co
       tma_prefetch_desc(&tmap_v);
       tma_prefetch_desc(&tmap_kvw);
       mbar_expect_tx(&bars[kBarQFull], kQ8Bytes);
-      tma_load_4d(smem + kOffQ8, &tmap_q8, &bars[kBarQFull], 0, m_blk * BLKQ, bh, 0);
+      if constexpr (kQK16) {  // 16-bit Q rows from [B,L,H,D]: two 64-column chunks of 128 rows x 128 B
+        tma_load_4d(smem + kOffQ8, &tmap_q8, &bars[kBarQFull], 0, hh, m_blk * BLKQ, b);
+        tma_load_4d(smem + kOffQ8 + kQ8Bytes / 2, &tmap_q8, &bars[kBarQFull], 64, hh, m_blk * BLKQ, b);
+      } else {
+        tma_load_4d(smem + kOffQ8, &tmap_q8, &bars[kBarQFull], 0, m_blk * BLKQ, bh, 0);
+      }
       for (int j = 0; j < T_blocks; ++j) {
         const int st = j % kStages;
         const uint32_t ph = ((j / kStages) & 1) ^ 1;
         const int blk = s_lut[j];
         mbar_wait(&bars[kBarKEmpty + st], ph);
         mbar_expect_tx(&bars[kBarKFull + st], kK8Bytes);
-        tma_load_4d(smem + kOffK8 + st * kK8Bytes, &tmap_k8, &bars[kBarKFull + st], 0, blk * BLKK, bh, 0);
+        if constexpr (kQK16) {
+          tma_load_4d(smem + kOffK8 + st * kK8Bytes, &tmap_k8, &bars[kBarKFull + st], 0, hh, blk * BLKK, b);
+          tma_load_4d(smem + kOffK8 + st * kK8Bytes + kK8Bytes / 2, &tmap_k8, &bars[kBarKFull + st], 64, hh, blk * BLKK, b);
+        } else {
+          tma_load_4d(smem + kOffK8 + st * kK8Bytes, &tmap_k8, &bars[kBarKFull + st], 0, blk * BLKK, bh, 0);
+        }
         mbar_wait(&bars[kBarVEmpty + st], ph);
         mbar_expect_tx(&bars[kBarVFull + st], kVBytes);
         uint8_t* sv = smem + kOffV + st * kVBytes;
@@ -162,6 +182,8 @@ sla_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q8, const __grid_co
     // =============================================================== MMA issuer
     if (lane == 0) {
       constexpr uint32_t idesc_qk = make_idesc(kDFmtS32, kFmtS8, kFmtS8, 0, 0, BLKQ, BLKK);
+      constexpr uint32_t f16fmt = std::is_same<T, __nv_bfloat16>::value ? kFmtBF16 : kFmtF16;
+      constexpr uint32_t idesc_qk16 = make_idesc(kDFmtF32, f16fmt, f16fmt, 0, 0, BLKQ, BLKK);
       constexpr uint32_t idesc_pv = make_idesc(kDFmtF32, kFmtBF16, kFmtBF16, 0, 1, BLKQ, D);
       constexpr uint32_t idesc_lin = make_idesc(kDFmtF32, kFmtBF16, kFmtBF16, 0, 0, BLKQ, D);
       constexpr uint32_t idesc_pv16 = make_idesc(kDFmtF32, kFmtF16, kFmtF16, 0, 1, BLKQ, D);
@@ -194,10 +216,19 @@ sla_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q8, const __grid_co
         mbar_wait(&bars[kBarSEmpty + sb], ((j >> 1) & 1) ^ 1);
         tc_fence_after_sync();
         const uint64_t kdesc = make_desc_kmajor_sw128(sbase + kOffK8 + st * kK8Bytes);
+        if constexpr (kQK16) {
 #pragma unroll
-        for (int ks = 0; ks < D / 32; ++ks)
-          umma_i8_ss(tmem_base + kColS + sb * BLKK, qdesc + uint64_t(ks * 2), kdesc + uint64_t(ks * 2), idesc_qk,
-                     ks > 0 ? 1u : 0u);
+          for (int ks = 0; ks < D / 16; ++ks) {  // K = 16 elements per MMA: chunk ks/4, +32 bytes per step inside the chunk
+            const uint64_t qd = make_desc_kmajor_sw128(sbase + kOffQ8 + (ks >> 2) * (kQ8Bytes / 2)) + uint64_t((ks & 3) * 2);
+            const uint64_t kd = make_desc_kmajor_sw128(sbase + kOffK8 + st * kK8Bytes + (ks >> 2) * (kK8Bytes / 2)) + uint64_t((ks & 3) * 2);
+            umma_f16_ss(tmem_base + kColS + sb * BLKK, qd, kd, idesc_qk16, ks > 0 ? 1u : 0u);
+          }
+        } else {
+#pragma unroll
+          for (int ks = 0; ks < D / 32; ++ks)
+            umma_i8_ss(tmem_base + kColS + sb * BLKK, qdesc + uint64_t(ks * 2), kdesc + uint64_t(ks * 2), idesc_qk,
+                       ks > 0 ? 1u : 0u);
+        }
         umma_commit(&bars[kBarSFull + sb]);
         umma_commit(&bars[kBarKEmpty + st]);
         if (j > 0) issue_pv(j - 1);
@@ -224,9 +255,12 @@ sla_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q8, const __grid_co
     const int r = warp * 32 + lane;                     // query row inside the block == TMEM lane
     const uint32_t lane_addr = uint32_t(warp * 32) << 16;
     const int64_t q_row = int64_t(m_blk) * BLKQ + r;
-    const float qsc = __ldg(p.q_scale + int64_t(bh) * p.mblk + m_blk) * p.sm_scale * kLog2e;
-    constexpr float kMagicF = 12582912.0f;              // 1.5 * 2^23: as_float(0x4B400000 + i) == kMagicF + i for |i| < 2^22
-    constexpr int kMagicI = 0x4B400000;
+    // INT8 path: S holds int32 dot products; as_float(s + kMagicI) == kMagicF + s exactly, folded into the exponent's bias.
+    // 16-bit path: S already holds fp32 scores: the same expressions with a zero magic constant.
+    const float qsc = (kQK16 ? 1.0f : __ldg(p.q_scale + int64_t(bh) * p.mblk + m_blk)) * p.sm_scale * kLog2e;
+    constexpr float kMagicF = kQK16 ? 0.0f : 12582912.0f;   // 1.5 * 2^23: as_float(0x4B400000 + i) == kMagicF + i for |i| < 2^22
+    constexpr int kMagicI = kQK16 ? 0 : 0x4B400000;
+    constexpr uint32_t kMasked = kQK16 ? 0xFF800000u : 0x80000000u;   // -inf | INT_MIN
     uint8_t* const sP = smem + kOffP;
 
     long long* trace_base = nullptr;
@@ -260,22 +294,35 @@ sla_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q8, const __grid_co
       if (valid < BLKK) {
 #pragma unroll
         for (int c = 0; c < 32; ++c) {
-          if (c >= valid) s0[c] = 0x80000000u;
-          if (c + 32 >= valid) s1[c] = 0x80000000u;
+          if (c >= valid) s0[c] = kMasked;
+          if (c + 32 >= valid) s1[c] = kMasked;
         }
       }
       // four independent max chains (depth 8 instead of 32: only two softmax warps share a scheduler, so serial
       // dependency chains, not issue slots, were the limiter)
-      int mxa = -2147483647 - 1, mxb = mxa, mxc = mxa, mxd = mxa;
+      float m_blk_f;
+      if constexpr (kQK16) {
+        float fa = -INFINITY, fb = fa, fc = fa, fd = fa;
 #pragma unroll
-      for (int c = 0; c < 32; c += 4) {
-        mxa = __vimax3_s32(mxa, static_cast<int>(s0[c]), static_cast<int>(s0[c + 1]));
-        mxb = __vimax3_s32(mxb, static_cast<int>(s0[c + 2]), static_cast<int>(s0[c + 3]));
-        mxc = __vimax3_s32(mxc, static_cast<int>(s1[c]), static_cast<int>(s1[c + 1]));
-        mxd = __vimax3_s32(mxd, static_cast<int>(s1[c + 2]), static_cast<int>(s1[c + 3]));
+        for (int c = 0; c < 32; c += 4) {
+          fa = fmaxf(fa, fmaxf(__uint_as_float(s0[c]), __uint_as_float(s0[c + 1])));
+          fb = fmaxf(fb, fmaxf(__uint_as_float(s0[c + 2]), __uint_as_float(s0[c + 3])));
+          fc = fmaxf(fc, fmaxf(__uint_as_float(s1[c]), __uint_as_float(s1[c + 1])));
+          fd = fmaxf(fd, fmaxf(__uint_as_float(s1[c + 2]), __uint_as_float(s1[c + 3])));
+        }
+        m_blk_f = fmaxf(fmaxf(fa, fb), fmaxf(fc, fd)) * sc;
+      } else {
+        int mxa = -2147483647 - 1, mxb = mxa, mxc = mxa, mxd = mxa;
+#pragma unroll
+        for (int c = 0; c < 32; c += 4) {
+          mxa = __vimax3_s32(mxa, static_cast<int>(s0[c]), static_cast<int>(s0[c + 1]));
+          mxb = __vimax3_s32(mxb, static_cast<int>(s0[c + 2]), static_cast<int>(s0[c + 3]));
+          mxc = __vimax3_s32(mxc, static_cast<int>(s1[c]), static_cast<int>(s1[c + 1]));
+          mxd = __vimax3_s32(mxd, static_cast<int>(s1[c + 2]), static_cast<int>(s1[c + 3]));
+        }
+        const int mx = max(max(mxa, mxb), max(mxc, mxd));
+        m_blk_f = static_cast<float>(mx) * sc;
       }
-      const int mx = max(max(mxa, mxb), max(mxc, mxd));
-      const float m_blk_f = static_cast<float>(mx) * sc;
 
       // ---- lazy rescale of the O accumulator (warp-uniform decision: tcgen05.ld/st are warp-collective)
       const bool grow = m_blk_f > m_used + kRescaleThreshold;
@@ -338,7 +385,7 @@ sla_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q8, const __grid_co
       if (valid < BLKK) {
         // exact fix-up of the ragged block: every masked column produced the same p (same INT_MIN input); remove it
         // from the row sum and clear its 16-bit slot so the tensor core multiplies V's zero-filled rows by zero
-        const float pm = fast_exp2(fmaf(__int_as_float(static_cast<int>(0x80000000u) + kMagicI), sc, cbias));
+        const float pm = fast_exp2(fmaf(__int_as_float(static_cast<int>(kMasked) + kMagicI), sc, cbias));
         psum -= static_cast<float>(BLKK - valid) * pm;
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
@@ -491,37 +538,49 @@ extern "C" int tdb200_debug_set_attn_trace(long long* trace_or_null) {
   return tdb::check_cuda(cudaMemcpyToSymbol(g_attn_trace, &trace_or_null, sizeof(trace_or_null)), "cudaMemcpyToSymbol(g_attn_trace)");
 }
 
-extern "C" int tdb200_sla_attn_fwd(const int8_t* q_i8, const float* q_scale, const int8_t* k_i8, const float* k_scale,
-                                   const void* v, const void* q, int dtype, const int32_t* lut, int64_t topk,
-                                   const void* kvw, const float* ksum, const float* proj_b, void* out, int64_t b,
-                                   int64_t l, int64_t lk, int64_t h, int64_t d, float sm_scale, void* stream) {
+template <bool kQK16>
+static int launch_v1(const void* q_op, const float* q_scale, const void* k_op, const float* k_scale, const void* v, const void* q,
+                     int dtype, const int32_t* lut, int64_t topk, const void* kvw, const float* ksum, const float* proj_b,
+                     void* out, int64_t b, int64_t l, int64_t lk, int64_t h, int64_t d, float sm_scale, void* stream) {
   using namespace tdb;
-  if (!q_i8 || !q_scale || !k_i8 || !k_scale || !v || !q || !lut || !kvw || !ksum || !proj_b || !out)
+  using L = Lay<kQK16>;
+  if (!q_op || !k_op || !v || !q || !lut || !kvw || !ksum || !proj_b || !out || (!kQK16 && (!q_scale || !k_scale)))
     return fail(TDB200_ERR_INVALID_ARG, "sla_attn_fwd: null pointer");
   if (b <= 0 || l <= 0 || lk <= 0 || h <= 0) return fail(TDB200_ERR_INVALID_ARG, "sla_attn_fwd: bad shape");
-  if (d != D) return fail(TDB200_ERR_UNSUPPORTED, "sla_attn_fwd: head dim %lld (this build implements d=128)", (long long)d);
+  if (d != D) return fail(TDB200_ERR_UNSUPPORTED, "sla_attn_fwd: head dim %lld (this kernel implements d=128)", (long long)d);
   const int64_t mblk = cdiv64(l, BLKQ), nblk = cdiv64(lk, BLKK);
   if (topk <= 0 || topk > nblk) return fail(TDB200_ERR_INVALID_ARG, "sla_attn_fwd: topk=%lld outside [1, %lld]", (long long)topk, (long long)nblk);
   if (nblk > 65535 || h > 65535 || b > 65535) return fail(TDB200_ERR_UNSUPPORTED, "sla_attn_fwd: dimension too large");
   const size_t lut_bytes = ((size_t(topk) * 2 + 15) & ~size_t(15)) + size_t(topk) * 4;
   static const bool one_cta_per_sm = getenv("TDB200_ATTN_ONE_CTA_PER_SM") != nullptr;  // diagnostics: timeline without a sibling CTA
-  const size_t smem = 1024 + kOffLut + lut_bytes + (one_cta_per_sm ? 64 * 1024 : 0);
+  const size_t smem = 1024 + L::kOffLut + lut_bytes + ((one_cta_per_sm && !kQK16) ? 64 * 1024 : 0);
   if (smem > 227 * 1024) return fail(TDB200_ERR_UNSUPPORTED, "sla_attn_fwd: topk=%lld too large for on-chip LUT", (long long)topk);
   if (int rc = require_sm100()) return rc;
 
   const CUtensorMapDataType t16 = dtype == TDB200_DTYPE_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
   CUtensorMap tq, tk, tv, tw;
-  {
-    const uint64_t dims[4] = {uint64_t(d), uint64_t(l), uint64_t(b * h), 1};
-    const uint64_t str[3] = {uint64_t(d), uint64_t(l * d), uint64_t(b * h * l * d)};
-    const uint32_t box[4] = {D, BLKQ, 1, 1};
-    if (int rc = make_tmap_4d(&tq, q_i8, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, dims, str, box)) return rc;
-  }
-  {
-    const uint64_t dims[4] = {uint64_t(d), uint64_t(lk), uint64_t(b * h), 1};
-    const uint64_t str[3] = {uint64_t(d), uint64_t(lk * d), uint64_t(b * h * lk * d)};
-    const uint32_t box[4] = {D, BLKK, 1, 1};
-    if (int rc = make_tmap_4d(&tk, k_i8, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, dims, str, box)) return rc;
+  if (kQK16) {  // 16-bit Q / K rows in the module layout [b, l, h, d]
+    const uint64_t dq[4] = {uint64_t(d), uint64_t(h), uint64_t(l), uint64_t(b)};
+    const uint64_t sq[3] = {uint64_t(d * 2), uint64_t(h * d * 2), uint64_t(l * h * d * 2)};
+    const uint32_t bq[4] = {64, 1, BLKQ, 1};
+    if (int rc = make_tmap_4d(&tq, q_op, t16, 2, dq, sq, bq)) return rc;
+    const uint64_t dk[4] = {uint64_t(d), uint64_t(h), uint64_t(lk), uint64_t(b)};
+    const uint64_t sk[3] = {uint64_t(d * 2), uint64_t(h * d * 2), uint64_t(lk * h * d * 2)};
+    const uint32_t bk[4] = {64, 1, BLKK, 1};
+    if (int rc = make_tmap_4d(&tk, k_op, t16, 2, dk, sk, bk)) return rc;
+  } else {
+    {
+      const uint64_t dims[4] = {uint64_t(d), uint64_t(l), uint64_t(b * h), 1};
+      const uint64_t str[3] = {uint64_t(d), uint64_t(l * d), uint64_t(b * h * l * d)};
+      const uint32_t box[4] = {D, BLKQ, 1, 1};
+      if (int rc = make_tmap_4d(&tq, q_op, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, dims, str, box)) return rc;
+    }
+    {
+      const uint64_t dims[4] = {uint64_t(d), uint64_t(lk), uint64_t(b * h), 1};
+      const uint64_t str[3] = {uint64_t(d), uint64_t(lk * d), uint64_t(b * h * lk * d)};
+      const uint32_t box[4] = {D, BLKK, 1, 1};
+      if (int rc = make_tmap_4d(&tk, k_op, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, dims, str, box)) return rc;
+    }
   }
   {
     const uint64_t dims[4] = {uint64_t(d), uint64_t(h), uint64_t(lk), uint64_t(b)};
@@ -554,14 +613,27 @@ extern "C" int tdb200_sla_attn_fwd(const int8_t* q_i8, const float* q_scale, con
   cudaStream_t st = static_cast<cudaStream_t>(stream);
 #define TDB_ATTN(T)                                                                                                   \
   do {                                                                                                                \
-    if (int rc = check_cuda(cudaFuncSetAttribute(sla_attn_fwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+    if (int rc = check_cuda(cudaFuncSetAttribute(sla_attn_fwd_kernel<T, kQK16>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                                  static_cast<int>(smem)), "cudaFuncSetAttribute(sla_attn)"))        \
       return rc;                                                                                                      \
-    sla_attn_fwd_kernel<T><<<grid, kThreads, smem, st>>>(tq, tk, tv, tw, p);                                          \
+    sla_attn_fwd_kernel<T, kQK16><<<grid, kThreads, smem, st>>>(tq, tk, tv, tw, p);                                   \
     return check_launch("sla_attn_fwd_kernel");                                                                       \
   } while (0)
   if (dtype == TDB200_DTYPE_BF16) TDB_ATTN(__nv_bfloat16);
   if (dtype == TDB200_DTYPE_FP16) TDB_ATTN(__half);
 #undef TDB_ATTN
   return fail(TDB200_ERR_UNSUPPORTED, "sla_attn_fwd: dtype tag %d", dtype);
+}
+
+extern "C" int tdb200_sla_attn_fwd(const int8_t* q_i8, const float* q_scale, const int8_t* k_i8, const float* k_scale,
+                                   const void* v, const void* q, int dtype, const int32_t* lut, int64_t topk,
+                                   const void* kvw, const float* ksum, const float* proj_b, void* out, int64_t b,
+                                   int64_t l, int64_t lk, int64_t h, int64_t d, float sm_scale, void* stream) {
+  return launch_v1<false>(q_i8, q_scale, k_i8, k_scale, v, q, dtype, lut, topk, kvw, ksum, proj_b, out, b, l, lk, h, d, sm_scale, stream);
+}
+
+extern "C" int tdb200_sla_attn_fwd_qk16(const void* q, const void* k, const void* v, int dtype, const int32_t* lut, int64_t topk,
+                                        const void* kvw, const float* ksum, const float* proj_b, void* out, int64_t b,
+                                        int64_t l, int64_t lk, int64_t h, int64_t d, float sm_scale, void* stream) {
+  return launch_v1<true>(q, nullptr, k, nullptr, v, q, dtype, lut, topk, kvw, ksum, proj_b, out, b, l, lk, h, d, sm_scale, stream);
 }

@@ -41,6 +41,19 @@ def quant_cuda(x: torch.Tensor, out_q: Optional[torch.Tensor] = None,
     return out_q, out_s
 
 
+def gelu_quant_cuda(x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """quant_cuda(gelu_tanh(x)) in one pass over x [M,K] bf16/fp16 (the FFN activation feeding the down projection)."""
+    require_cuda(x)
+    if x.dtype not in DTYPE_TAG or x.dim() != 2 or not x.is_contiguous():
+        raise RuntimeError("gelu_quant_cuda expects a contiguous 2-D bf16/fp16 tensor")
+    m, k = x.shape
+    out_q = torch.empty((m, k), dtype=torch.int8, device=x.device)
+    out_s = torch.empty((_cdiv(m, 128), _cdiv(k, 128)), dtype=torch.float32, device=x.device)
+    check(lib().tdb200_gelu_quant_int8_block128(ptr(x), DTYPE_TAG[x.dtype], m, k, ptr(out_q), ptr(out_s),
+                                                stream_ptr(x.device)), "gelu_quant_cuda")
+    return out_q, out_s
+
+
 GEMM_TIMER = None  # bench.py installs a callable(m, n, k) -> context manager to time GEMM launches with CUDA events
 
 
