@@ -181,9 +181,10 @@ def test_gelu_epilogue_vs_oracle_gelu(cuda, m, n, k):
     ref = F.gelu(pre, approximate="tanh")                                   # bf16 in, fp32 opmath, bf16 out
     got = c.cpu()
     # torch evaluates 0.5 x (1 + tanh(u)) in fp32: in the negative tail 1 + tanh(u) cancels and torch's own result is only
-    # good to ~1e-7 absolute; the kernel evaluates x * sigmoid(2u) (no cancellation).  So: one ulp of T, or 1e-6 absolute.
+    # good to ~1e-7 absolute; the kernel evaluates x * sigmoid(2u) (no cancellation).  So: one ulp of T (<= 2^-7 relative for
+    # an 8-bit significand), or 1e-6 absolute.
     diff = (got.float() - ref.float()).abs()
-    ok = diff <= torch.maximum(2.0 ** -8 * ref.float().abs(), torch.tensor(1e-6))
+    ok = diff <= torch.maximum(2.0 ** -7 * ref.float().abs(), torch.tensor(1e-6))
     assert ok.all(), (diff[~ok].max().item(), (~ok).sum().item())
     big = ref.float().abs() > 1e-3
     same = got.view(torch.int16)[big] == ref.view(torch.int16)[big]

@@ -20,16 +20,13 @@ constexpr int kPasses = kBlk / kRowsPerPass;     // 8
 // math, one rounding, rcm/networks/wan2pt1.py:375) is quantised instead of x.  gelu_tanh(x) = x * sigmoid(2u),
 // u = sqrt(2/pi)(x + 0.044715 x^3), evaluated as x / (1 + 2^z) with ex2.approx + rcp.approx (relative error ~2^-21 everywhere,
 // including the negative tail where 1 + tanh(u) cancels).
-// sigmoid(2u(x)) = 1 / (1 + 2^z), z = -2 log2(e) sqrt(2/pi) (x + 0.044715 x^3).  One MUFU (ex2); the reciprocal runs on the FMA pipe
-// (integer-trick seed + three Newton steps, relative error < 1e-6), because the XU pipe is what bounds this kernel: with a second
-// MUFU per element it ran at 0.47 of the HBM peak (profiles/r02_microbench_prologue.jsonl).
+// sigmoid(2u(x)) = 1 / (1 + 2^z), z = -2 log2(e) sqrt(2/pi) (x + 0.044715 x^3): ex2.approx + rcp.approx (relative error ~2^-21
+// everywhere, no cancellation in the negative tail).  Measured alternatives (profiles/r02_microbench_prologue.jsonl, shape A
+// 32760 x 8960): this form 0.285 ms; reciprocal by three Newton steps on the FMA pipe instead of the second MUFU 0.371 ms
+// (the kernel is bound by issue slots, not by the XU pipe).
 __device__ __forceinline__ float sigmoid_2u(float x) {
-  const float z = fminf(x * fmaf(-0.10294324f, x * x, -2.3022082f), 120.0f);
-  const float d = 1.0f + fast_exp2(z);                       // in [1, 2^120]
-  float r = __int_as_float(0x7EF311C7 - __float_as_int(d));   // 1/d within 12 %
-  r = r * fmaf(-d, r, 2.0f);
-  r = r * fmaf(-d, r, 2.0f);
-  r = r * fmaf(-d, r, 2.0f);
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + fast_exp2(x * fmaf(-0.10294324f, x * x, -2.3022082f))));
   return r;
 }
 

@@ -84,7 +84,7 @@ template <typename T, bool kQK16>
 __global__ void __launch_bounds__(kThreads, 2)
 sla_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q8, const __grid_constant__ CUtensorMap tmap_k8,
                     const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_kvw,
-                    AttnParams p) {
+                    const __grid_constant__ CUtensorMap tmap_out, AttnParams p) {
   using L = Lay<kQK16>;
   constexpr int kStages = L::kStages;
   constexpr uint32_t kOffQ8 = L::kOffQ, kOffK8 = L::kOffK, kOffV = L::kOffV, kOffP = L::kOffP, kOffBars = L::kOffBars, kOffLut = L::kOffLut;
@@ -143,6 +143,7 @@ sla_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q8, const __grid_co
       tma_prefetch_desc(&tmap_k8);
       tma_prefetch_desc(&tmap_v);
       tma_prefetch_desc(&tmap_kvw);
+      tma_prefetch_desc(&tmap_out);
       mbar_expect_tx(&bars[kBarQFull], kQ8Bytes);
       if constexpr (kQK16) {  // 16-bit Q rows from [B,L,H,D]: two 64-column chunks of 128 rows x 128 B
         tma_load_4d(smem + kOffQ8, &tmap_q8, &bars[kBarQFull], 0, hh, m_blk * BLKQ, b);
@@ -235,18 +236,19 @@ sla_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q8, const __grid_co
       }
       issue_pv(T_blocks - 1);
 
-      // ---- linear branch: OL[128 x 128] = phi(Q)[128 x 128] . KVW^T, written over the S columns
+      // ---- linear branch, folded into the P.V accumulator:  O += A[128 x 128] . KVW^T  with  A = phi(q) * l / den  (so that
+      //      O / l afterwards equals  softmax-part + phi(q).KVW^T / den)
       mbar_wait(&bars[kBarPhiFull], 0);
       mbar_wait(&bars[kBarKvwFull], 0);
       tc_fence_after_sync();
 #pragma unroll
       for (int ks = 0; ks < D / 16; ++ks) {
-        // 64-wide K chunk (phi: chunk 0 in the P buffer, chunk 1 in the freed Q tile; KVW: the two V stages the last
+        // 64-wide K chunk (A: chunk 0 in the P buffer, chunk 1 in the freed Q tile; KVW: the two V stages the last
         // key block did not use), +32 B per K=16 step
         const uint64_t adesc = make_desc_kmajor_sw128(sbase + ((ks >> 2) ? kOffQ8 : kOffP) + (ks & 3) * 32);
         const uint64_t bdesc =
             make_desc_kmajor_sw128(sbase + kOffV + ((T_blocks + (ks >> 2)) % kStages) * kVBytes + (ks & 3) * 32);
-        umma_f16_ss(tmem_base + kColS, adesc, bdesc, id_lin, ks > 0 ? 1u : 0u);
+        umma_f16_ss(tmem_base + kColO, adesc, bdesc, id_lin, 1u);
       }
       umma_commit(&bars[kBarOlFull]);
     }
@@ -262,6 +264,11 @@ sla_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q8, const __grid_co
     constexpr int kMagicI = kQK16 ? 0 : 0x4B400000;
     constexpr uint32_t kMasked = kQK16 ? 0xFF800000u : 0x80000000u;   // -inf | INT_MIN
     uint8_t* const sP = smem + kOffP;
+    {  // the row of q this thread needs for the linear branch after the loop: start moving it towards L2 now
+      const T* qrow = static_cast<const T*>(p.q) + ((int64_t(b) * p.l + (q_row < p.l ? q_row : p.l - 1)) * p.h + hh) * D;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(qrow));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(qrow + 64));
+    }
 
     long long* trace_base = nullptr;
     const bool tracing = g_attn_trace != nullptr && warp == 0 && lane == 0 && hh == 0 && b == 0 && (m_blk == 1 || m_blk == 3);
@@ -418,108 +425,89 @@ sla_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q8, const __grid_co
     if (tracing) trace_base[63 * 8 + 7] = clock64();  // loop exit
     if (tracing) trace_base[62 * 8 + 2] = clock64();
 
-    // ---- linear branch operand: phi(q) = softmax over D of this thread's query row (SLA/core.py:243), rounded to T
-    float den = 1e-5f;
-    uint32_t phi[D / 2];  // holds the raw q row first, then phi(q), chunk by chunk in place
+    // ---- linear branch operand (SLA/core.py:243): e_j = exp(q_j - max_j q), ONE exponential per element kept in fp32 registers,
+    //      E = sum e_j, F = sum e_j * ksum_j;  phi_j = e_j / E,  den = 1e-5 + sum_j phi_j ksum_j = 1e-5 + F / E;
+    //      the tensor core receives A_j = T(phi_j * l / den), so that O + A.KVW^T = l * (O/l + phi.KVW^T/den).
+    uint32_t aw[D / 2];
     {
       const T* qrow = static_cast<const T*>(p.q) + ((int64_t(b) * p.l + (q_row < p.l ? q_row : p.l - 1)) * p.h + hh) * D;
       float qm0 = -INFINITY, qm1 = -INFINITY, qm2 = -INFINITY, qm3 = -INFINITY;
 #pragma unroll
       for (int c = 0; c < D / 8; ++c) {
         const uint4 raw = __ldg(reinterpret_cast<const uint4*>(qrow) + c);
-        phi[4 * c] = raw.x; phi[4 * c + 1] = raw.y; phi[4 * c + 2] = raw.z; phi[4 * c + 3] = raw.w;
+        aw[4 * c] = raw.x; aw[4 * c + 1] = raw.y; aw[4 * c + 2] = raw.z; aw[4 * c + 3] = raw.w;
         qm0 = fmaxf(qm0, fmaxf(F16Traits<T>::lo(raw.x), F16Traits<T>::hi(raw.x)));
         qm1 = fmaxf(qm1, fmaxf(F16Traits<T>::lo(raw.y), F16Traits<T>::hi(raw.y)));
         qm2 = fmaxf(qm2, fmaxf(F16Traits<T>::lo(raw.z), F16Traits<T>::hi(raw.z)));
         qm3 = fmaxf(qm3, fmaxf(F16Traits<T>::lo(raw.w), F16Traits<T>::hi(raw.w)));
       }
-      const float qmax = fmaxf(fmaxf(qm0, qm1), fmaxf(qm2, qm3));
-      const float qoff = qmax * kLog2e;
-      float qs0 = 0.f, qs1 = 0.f, qs2 = 0.f, qs3 = 0.f;  // independent chains (latency-bound otherwise)
-#pragma unroll
-      for (int i = 0; i < D / 2; i += 2) {
-        qs0 += fast_exp2(fmaf(F16Traits<T>::lo(phi[i]), kLog2e, -qoff));
-        qs1 += fast_exp2(fmaf(F16Traits<T>::hi(phi[i]), kLog2e, -qoff));
-        qs2 += fast_exp2(fmaf(F16Traits<T>::lo(phi[i + 1]), kLog2e, -qoff));
-        qs3 += fast_exp2(fmaf(F16Traits<T>::hi(phi[i + 1]), kLog2e, -qoff));
-      }
-      const float qinv = 1.0f / ((qs0 + qs1) + (qs2 + qs3));
+      const float qoff = fmaxf(fmaxf(qm0, qm1), fmaxf(qm2, qm3)) * kLog2e;
       const float* ks = p.ksum + int64_t(bh) * D;
-      float den1 = 0.f, den2 = 0.f, den3 = 0.f;
+      float e[D];
+      float e0 = 0.f, e1 = 0.f, e2 = 0.f, e3 = 0.f, f0 = 0.f, f1 = 0.f, f2 = 0.f, f3 = 0.f;  // independent chains
 #pragma unroll
       for (int i = 0; i < D / 2; i += 2) {
-        const float4 kv4 = __ldg(reinterpret_cast<const float4*>(ks + 2 * i));
-        const float a = F16Traits<T>::round(fast_exp2(fmaf(F16Traits<T>::lo(phi[i]), kLog2e, -qoff)) * qinv);
-        const float c2 = F16Traits<T>::round(fast_exp2(fmaf(F16Traits<T>::hi(phi[i]), kLog2e, -qoff)) * qinv);
-        const float a1 = F16Traits<T>::round(fast_exp2(fmaf(F16Traits<T>::lo(phi[i + 1]), kLog2e, -qoff)) * qinv);
-        const float c3 = F16Traits<T>::round(fast_exp2(fmaf(F16Traits<T>::hi(phi[i + 1]), kLog2e, -qoff)) * qinv);
-        den = fmaf(a, kv4.x, den);
-        den1 = fmaf(c2, kv4.y, den1);
-        den2 = fmaf(a1, kv4.z, den2);
-        den3 = fmaf(c3, kv4.w, den3);
-        phi[i] = F16Traits<T>::pack(a, c2);
-        phi[i + 1] = F16Traits<T>::pack(a1, c3);
+        const float4 k4 = __ldg(reinterpret_cast<const float4*>(ks + 2 * i));
+        e[2 * i] = fast_exp2(fmaf(F16Traits<T>::lo(aw[i]), kLog2e, -qoff));
+        e[2 * i + 1] = fast_exp2(fmaf(F16Traits<T>::hi(aw[i]), kLog2e, -qoff));
+        e[2 * i + 2] = fast_exp2(fmaf(F16Traits<T>::lo(aw[i + 1]), kLog2e, -qoff));
+        e[2 * i + 3] = fast_exp2(fmaf(F16Traits<T>::hi(aw[i + 1]), kLog2e, -qoff));
+        e0 += e[2 * i]; e1 += e[2 * i + 1]; e2 += e[2 * i + 2]; e3 += e[2 * i + 3];
+        f0 = fmaf(e[2 * i], k4.x, f0); f1 = fmaf(e[2 * i + 1], k4.y, f1);
+        f2 = fmaf(e[2 * i + 2], k4.z, f2); f3 = fmaf(e[2 * i + 3], k4.w, f3);
       }
-      den += (den1 + den2) + den3;
+      const float inv_e = 1.0f / ((e0 + e1) + (e2 + e3));
+      const float den = fmaf((f0 + f1) + (f2 + f3), inv_e, 1e-5f);
+      const float cscale = inv_e * l_sum / den;
+#pragma unroll
+      for (int i = 0; i < D / 2; ++i) aw[i] = F16Traits<T>::pack(e[2 * i] * cscale, e[2 * i + 1] * cscale);
     }
-    // all MMAs retired -> the P buffer and the Q tile may be overwritten with phi(q) (two 64-wide K chunks of 16 KB)
+    // all MMAs retired -> the P buffer and the Q tile may be overwritten with A (two 64-wide K chunks of 16 KB)
     mbar_wait(&bars[kBarPvDone], (T_blocks - 1) & 1);
     tc_fence_after_sync();
 #pragma unroll
     for (int c = 0; c < 16; ++c) {
       uint8_t* dst = ((c >> 3) ? smem + kOffQ8 : sP) + r * 128 + (((c & 7) ^ (r & 7)) << 4);
-      *reinterpret_cast<uint4*>(dst) = make_uint4(phi[4 * c], phi[4 * c + 1], phi[4 * c + 2], phi[4 * c + 3]);
+      *reinterpret_cast<uint4*>(dst) = make_uint4(aw[4 * c], aw[4 * c + 1], aw[4 * c + 2], aw[4 * c + 3]);
     }
     fence_proxy_async_smem();
     __syncwarp();
     if (lane == 0) mbar_arrive(&bars[kBarPhiFull]);
     if (tracing) trace_base[62 * 8 + 3] = clock64();
 
-    // ---- merge: out = T( O / l + OL / den + proj_b )
+    // ---- out = T( O / l + proj_b ): the two staging buffers (P buffer: columns 0-63, Q tile: columns 64-127; both free once the
+    //      linear MMA has retired) hold 128 rows x 128 bytes each in the 128B-swizzled TMA layout and leave as two box stores
+    //      (rows >= l are clipped by the tensor map)
     mbar_wait(&bars[kBarOlFull], 0);
     tc_fence_after_sync();
     if (tracing) trace_base[62 * 8 + 4] = clock64();
-    const float inv_l = 1.0f / l_sum, inv_den = 1.0f / den;
-    // Staging: rows 0-63 in the P buffer, rows 64-127 in the Q tile (both free once the linear MMA has retired); 256-byte
-    // rows, 16-byte chunk c of row r at (c ^ (r & 15)).  Each warp then writes its own 32 rows, two full rows per
-    // store instruction, instead of one row per lane.
-    uint8_t* stg = (r < 64 ? sP : smem + kOffQ8) + (r & 63) * 256;
+    const float inv_l = 1.0f / l_sum;
 #pragma unroll
     for (int c = 0; c < D / 32; ++c) {
-      uint32_t o[32], ol[32];
+      uint32_t o[32];
       tmem_ld_x32(tmem_base + lane_addr + kColO + c * 32, o);
-      tmem_ld_x32(tmem_base + lane_addr + kColS + c * 32, ol);
       tmem_ld_wait();
       const float4* pb4 = reinterpret_cast<const float4*>(p.proj_b + c * 32);
+      uint8_t* stg = ((c >> 1) ? smem + kOffQ8 : sP) + r * 128;
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
         const float4 b0 = __ldg(pb4 + 2 * g), b1 = __ldg(pb4 + 2 * g + 1);
-        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-        uint32_t w[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int e = g * 8 + 2 * i;
-          const float y0 = fmaf(__uint_as_float(o[e]), inv_l, fmaf(__uint_as_float(ol[e]), inv_den, bb[2 * i]));
-          const float y1 = fmaf(__uint_as_float(o[e + 1]), inv_l, fmaf(__uint_as_float(ol[e + 1]), inv_den, bb[2 * i + 1]));
-          w[i] = F16Traits<T>::pack(y0, y1);
-        }
-        const int ch = c * 4 + g;
-        *reinterpret_cast<uint4*>(stg + ((ch ^ (r & 15)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+        uint4 w;
+        w.x = F16Traits<T>::pack(fmaf(__uint_as_float(o[g * 8 + 0]), inv_l, b0.x), fmaf(__uint_as_float(o[g * 8 + 1]), inv_l, b0.y));
+        w.y = F16Traits<T>::pack(fmaf(__uint_as_float(o[g * 8 + 2]), inv_l, b0.z), fmaf(__uint_as_float(o[g * 8 + 3]), inv_l, b0.w));
+        w.z = F16Traits<T>::pack(fmaf(__uint_as_float(o[g * 8 + 4]), inv_l, b1.x), fmaf(__uint_as_float(o[g * 8 + 5]), inv_l, b1.y));
+        w.w = F16Traits<T>::pack(fmaf(__uint_as_float(o[g * 8 + 6]), inv_l, b1.z), fmaf(__uint_as_float(o[g * 8 + 7]), inv_l, b1.w));
+        const int ch = (c & 1) * 4 + g;                      // 16-byte chunk inside the 128-byte half row
+        *reinterpret_cast<uint4*>(stg + ((ch ^ (r & 7)) << 4)) = w;
       }
     }
-    __syncwarp();
-    {
-      const uint8_t* wbase = (warp < 2 ? sP : smem + kOffQ8) + (warp & 1) * 32 * 256;
-      const int cc = lane & 15;
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const int rr = 2 * i + (lane >> 4);                       // row within this warp's 32 rows
-        const int rg = (warp & 1) * 32 + rr;                      // row within the 64-row staging region
-        const uint4 v4 = *reinterpret_cast<const uint4*>(wbase + rr * 256 + ((cc ^ (rg & 15)) << 4));
-        const int64_t grow = int64_t(m_blk) * BLKQ + warp * 32 + rr;
-        if (grow < p.l)
-          stg_v4(static_cast<T*>(p.out) + ((int64_t(b) * p.l + grow) * p.h + hh) * D + cc * 8, v4);
-      }
+    fence_proxy_async_smem();
+    named_bar_sync(1, kSoftmaxWarps * 32);                   // all 128 rows are staged
+    if (threadIdx.x == 0) {
+      tma_store_4d(&tmap_out, sP, 0, hh, m_blk * BLKQ, b);
+      tma_store_4d(&tmap_out, smem + kOffQ8, 64, hh, m_blk * BLKQ, b);
+      tma_store_commit();
+      tma_store_wait_read<0>();                              // shared memory must outlive the reads of the store engine
     }
     if (tracing) trace_base[62 * 8 + 5] = clock64();
     tc_fence_before_sync();
@@ -594,6 +582,13 @@ static int launch_v1(const void* q_op, const float* q_scale, const void* k_op, c
     const uint32_t box[4] = {64, D, 1, 1};
     if (int rc = make_tmap_4d(&tw, kvw, t16, 2, dims, str, box)) return rc;
   }
+  CUtensorMap to;
+  {  // output tile store: [b, l, h, d] T, one box = 128 rows x 64 columns of one head
+    const uint64_t dims[4] = {uint64_t(d), uint64_t(h), uint64_t(l), uint64_t(b)};
+    const uint64_t str[3] = {uint64_t(d * 2), uint64_t(h * d * 2), uint64_t(l * h * d * 2)};
+    const uint32_t box[4] = {64, 1, BLKQ, 1};
+    if (int rc = make_tmap_4d(&to, out, t16, 2, dims, str, box)) return rc;
+  }
   AttnParams p;
   p.q_scale = q_scale;
   p.k_scale = k_scale;
@@ -616,7 +611,7 @@ static int launch_v1(const void* q_op, const float* q_scale, const void* k_op, c
     if (int rc = check_cuda(cudaFuncSetAttribute(sla_attn_fwd_kernel<T, kQK16>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                                  static_cast<int>(smem)), "cudaFuncSetAttribute(sla_attn)"))        \
       return rc;                                                                                                      \
-    sla_attn_fwd_kernel<T, kQK16><<<grid, kThreads, smem, st>>>(tq, tk, tv, tw, p);                                   \
+    sla_attn_fwd_kernel<T, kQK16><<<grid, kThreads, smem, st>>>(tq, tk, tv, tw, to, p);                               \
     return check_launch("sla_attn_fwd_kernel");                                                                       \
   } while (0)
   if (dtype == TDB200_DTYPE_BF16) TDB_ATTN(__nv_bfloat16);
