@@ -58,6 +58,7 @@ def _build(mm, dim, heads, ffn, layers, text_len, attention, topk):
     mm.replace_attention(m, attention, topk)
     m = m.to("cuda")
     mm.replace_linear_norm(m, replace_linear=True, replace_norm=True, quantize=True)
+    m = m.to("cuda")   # the FastNorm buffers are created on the host by from_*norm; create_model moves the net last, too (:139)
     with torch.no_grad():
         for blk in m.blocks:  # proj_l is zero-initialised (SLA/core.py:163-166): give the linear branch something to do
             blk.self_attn.attn_op.local_attn.proj_l.weight.normal_(0, 0.05)

@@ -378,6 +378,12 @@ struct F16Traits<__nv_bfloat16> {
     __nv_bfloat162 r = __hadd2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
     return *reinterpret_cast<uint32_t*>(&r);
   }
+  // per 16-bit lane max(acc, |v|)  (acc holds non-negative values)
+  static __device__ __forceinline__ uint32_t absmax2(uint32_t acc, uint32_t v) {
+    v &= 0x7FFF7FFFu;
+    __nv_bfloat162 r = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&acc), *reinterpret_cast<__nv_bfloat162*>(&v));
+    return *reinterpret_cast<uint32_t*>(&r);
+  }
 };
 template <>
 struct F16Traits<__half> {
@@ -394,6 +400,11 @@ struct F16Traits<__half> {
   static __device__ __forceinline__ float round(float a) { return __half2float(__float2half_rn(a)); }
   static __device__ __forceinline__ uint32_t add2(uint32_t a, uint32_t b) {
     __half2 r = __hadd2(*reinterpret_cast<__half2*>(&a), *reinterpret_cast<__half2*>(&b));
+    return *reinterpret_cast<uint32_t*>(&r);
+  }
+  static __device__ __forceinline__ uint32_t absmax2(uint32_t acc, uint32_t v) {
+    v &= 0x7FFF7FFFu;
+    __half2 r = __hmax2(*reinterpret_cast<__half2*>(&acc), *reinterpret_cast<__half2*>(&v));
     return *reinterpret_cast<uint32_t*>(&r);
   }
 };

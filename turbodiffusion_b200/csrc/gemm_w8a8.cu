@@ -183,6 +183,17 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const int half = warp >> 2;        // which 128-column half of the 256-wide tile
     const uint32_t lane_addr = uint32_t(q4 * 32) << 16;
     uint32_t it = 0, tile_it = 0;
+    // K-block 0 scales of the tile about to start: fetched while the previous tile's epilogue runs (they sat exposed in front of
+    // the first dequant before: ~600 clk of L2 latency per tile, 7 % of a K = 1536 tile)
+    float as_first = 0.f, bs_first = 0.f;
+    auto first_scales = [&](int work, float& a0, float& b0) {
+      int mt, nt;
+      tile_of(work, mt, nt);
+      const int64_t c0 = int64_t(nt) * BN + half * 128;
+      a0 = __ldg(p.a_s + int64_t(mt < p.m_tiles ? mt : p.m_tiles - 1) * p.k_blocks);
+      b0 = __ldg(p.b_s + (c0 < p.n ? (c0 >> 7) : 0) * p.k_blocks);
+    };
+    if (!kRowScale && work_first < p.total_tiles) first_scales(work_first, as_first, bs_first);
     for (int work = work_first; work < p.total_tiles; work += work_stride) {
       int m_tile, n_tile;
       tile_of(work, m_tile, n_tile);
@@ -263,7 +274,7 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
       // block scales are fetched one K-block ahead and only multiplied when used, so the global-load latency hides
       // behind the previous K-block's dequant instead of stalling in front of the barrier wait
-      float as_next = __ldg(as_row), bs_next = __ldg(bs_row);
+      float as_next = as_first, bs_next = bs_first;
       uint32_t ra[32], rb[32];
       auto dq32 = [&](uint32_t (&r)[32], int base, float scale) {
 #pragma unroll
@@ -354,6 +365,7 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       //      ROW, so the values go through the warp's private swizzled staging buffer and leave as TMA box stores (the
       //      tensor map clips rows >= m and columns >= n).  The buffer is reused one tile later: by then the store
       //      engine has read it (wait_group.read), and the warp never waits for the global write itself.
+      if (work + work_stride < p.total_tiles) first_scales(work + work_stride, as_first, bs_first);  // used after this epilogue
       const int64_t row0 = int64_t(m_tile) * BM + q4 * 32;
       uint8_t* stage = c_stage + warp * kCStageBytes;
       uint8_t* bslot = bias_slots + warp * kBiasSlot;
@@ -363,28 +375,46 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       if (p.out_q != nullptr) {
         // ---- fused a1: this thread's 128 values are one row of the 128x128 quant block (m_tile, col0/128).
         //      y = the T-rounded value the plain epilogue would store; amax over the block; q = sat_s8(rint(y*128/amax)).
+        //      Packed arithmetic throughout (16-bit x2 add / max, f32x2 multiply-add): this epilogue runs on the warps that
+        //      dequantise, so its issue slots are on the tile's critical path.  The T-rounded values live in the first 64
+        //      accumulator registers as packed pairs between the two passes.
         const bool row_in = row0 + lane < p.m;
-        float amax = 1e-8f;
+        uint32_t amax2 = 0u;
+        const float2 gc1 = make_float2(0.7978845608028654f, 0.7978845608028654f);
+        const float2 gc3 = make_float2(0.7978845608028654f * 0.044715f, 0.7978845608028654f * 0.044715f);
+        const float2 ghalf = make_float2(0.5f, 0.5f);
+        uint32_t yw[64];
 #pragma unroll
         for (int ch = 0; ch < 16; ++ch) {
           const uint4 b4 = *reinterpret_cast<const uint4*>(bslot + ch * 16);
           const uint32_t bw[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float y = acc[ch * 8 + j];
-            if (bias != nullptr) y = F16Traits<T>::round(y) + ((j & 1) ? F16Traits<T>::hi(bw[j >> 1]) : F16Traits<T>::lo(bw[j >> 1]));
-            if (act_gelu) y = gelu(F16Traits<T>::round(y));
-            y = (row_in && half_active) ? F16Traits<T>::round(y) : 0.f;
-            acc[ch * 8 + j] = y;
-            amax = fmaxf(amax, fabsf(y));
+          for (int j = 0; j < 4; ++j) {
+            uint32_t y = F16Traits<T>::pack(acc[ch * 8 + 2 * j], acc[ch * 8 + 2 * j + 1]);   // T(acc)
+            if (bias != nullptr) y = F16Traits<T>::add2(y, bw[j]);                            // T(T(acc) + bias)
+            if (act_gelu) {   // T(gelu_tanh(.)): u = x (c1 + c3 x^2), 0.5 x (1 + tanh u) = fma(0.5 x, tanh u, 0.5 x)
+              const float2 xv = make_float2(F16Traits<T>::lo(y), F16Traits<T>::hi(y));
+              const float2 u = __fmul2_rn(__ffma2_rn(__fmul2_rn(xv, xv), gc3, gc1), xv);
+              float2 t;
+              asm("tanh.approx.f32 %0, %1;" : "=f"(t.x) : "f"(u.x));
+              asm("tanh.approx.f32 %0, %1;" : "=f"(t.y) : "f"(u.y));
+              const float2 hx = __fmul2_rn(xv, ghalf);
+              const float2 g = __ffma2_rn(hx, t, hx);
+              y = F16Traits<T>::pack(g.x, g.y);
+            }
+            if (!(row_in && half_active)) y = 0u;
+            yw[ch * 4 + j] = y;
+            amax2 = F16Traits<T>::absmax2(amax2, y);
           }
         }
+        float amax = fmaxf(1e-8f, fmaxf(F16Traits<T>::lo(amax2), F16Traits<T>::hi(amax2)));
         amax = warp_max(amax);
         if (lane == 0) amax_x[warp] = amax;
         named_bar_sync(1 + half, 128);  // the 4 warps (lane quarters) of this 128-column half
 #pragma unroll
         for (int w = 0; w < 4; ++w) amax = fmaxf(amax, amax_x[half * 4 + w]);
         const float r = __fdiv_rn(128.0f, amax);
+        const float2 r2 = make_float2(r, r);
         if (q4 == 0 && lane == 0 && half_active && int64_t(m_tile) * BM < p.m)
           p.out_s[int64_t(m_tile) * (p.n >> 7) + (col0 >> 7)] = amax * 0.0078125f;
 #pragma unroll
@@ -394,10 +424,13 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           for (int j = 0; j < 4; ++j) {
             uint32_t word = 0;
 #pragma unroll
-            for (int b = 0; b < 4; ++b) {
-              int qv;
-              asm("cvt.rni.sat.s8.f32 %0, %1;" : "=r"(qv) : "f"(__fmul_rn(acc[ch * 16 + j * 4 + b], r)));
-              word |= (static_cast<uint32_t>(qv) & 0xFFu) << (8 * b);
+            for (int b = 0; b < 2; ++b) {
+              const uint32_t y = yw[ch * 8 + j * 2 + b];
+              const float2 v = __fmul2_rn(make_float2(F16Traits<T>::lo(y), F16Traits<T>::hi(y)), r2);
+              int q0, q1;
+              asm("cvt.rni.sat.s8.f32 %0, %1;" : "=r"(q0) : "f"(v.x));
+              asm("cvt.rni.sat.s8.f32 %0, %1;" : "=r"(q1) : "f"(v.y));
+              word |= ((static_cast<uint32_t>(q0) & 0xFFu) | ((static_cast<uint32_t>(q1) & 0xFFu) << 8)) << (16 * b);
             }
             w[j] = word;
           }

@@ -54,13 +54,23 @@ __global__ void __launch_bounds__(256) kmean_partial_kernel(const T* __restrict_
 }
 
 // ---- stage 2: fixed-order reduction of the partials -> kmean [b,h,d] fp32 -------------------------------------
-__global__ void kmean_final_kernel(const float* __restrict__ partial, float* __restrict__ kmean, int64_t l, int chunks,
-                                   int d) {
+// 1024 threads per (b,h): thread = (group g, column); group g adds chunks g, g+G, g+2G, ... in order, the G group sums are
+// combined in index order through shared memory (deterministic).  One CTA per head used to walk all chunks serially: 14 us of
+// pure load latency per call.
+__global__ void __launch_bounds__(1024) kmean_final_kernel(const float* __restrict__ partial, float* __restrict__ kmean, int64_t l,
+                                                           int chunks, int d) {
+  __shared__ float red[1024];
   const int bh = blockIdx.x;
-  for (int col = threadIdx.x; col < d; col += blockDim.x) {
-    float s = 0.f;
-    for (int ch = 0; ch < chunks; ++ch) s += partial[(int64_t(bh) * chunks + ch) * d + col];
-    kmean[int64_t(bh) * d + col] = s / static_cast<float>(l);
+  const int groups = 1024 / d;                 // 8 for d = 128, 16 for d = 64
+  const int col = threadIdx.x % d, g = threadIdx.x / d;
+  float s = 0.f;
+  for (int ch = g; ch < chunks; ch += groups) s += partial[(int64_t(bh) * chunks + ch) * d + col];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.x < d) {
+    float t = 0.f;
+    for (int gg = 0; gg < groups; ++gg) t += red[gg * d + threadIdx.x];
+    kmean[int64_t(bh) * d + threadIdx.x] = t / static_cast<float>(l);
   }
 }
 
@@ -126,6 +136,7 @@ __global__ void __launch_bounds__(ROWS* D / 64) pool_quant_kernel(const T* __res
 #pragma unroll
   for (int w = 0; w < THREADS / 32; ++w) amax = fmaxf(amax, warp_amax[w]);
   const float sc = __fadd_rn(amax / 127.0f, 1e-7f);
+  const float rinv = __frcp_rn(sc);
   if (threadIdx.x == 0) scale[bh * nblk + blk] = sc;
 
 #pragma unroll
@@ -134,7 +145,10 @@ __global__ void __launch_bounds__(ROWS* D / 64) pool_quant_kernel(const T* __res
     uint32_t lo = 0, hi = 0;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      float y = __fdiv_rn(v[p][j], sc);
+      // x / sc, correctly rounded, without the per-element division sequence: one reciprocal per block and Markstein's
+      // correction (q0 = x*r; q = q0 + (x - q0*sc)*r with fused multiply-adds equals RN(x/sc) for these magnitudes)
+      const float q0 = __fmul_rn(v[p][j], rinv);
+      float y = __fmaf_rn(__fmaf_rn(-q0, sc, v[p][j]), rinv, q0);
       y = __fadd_rn(y, y >= 0.f ? 0.5f : -0.5f);
       int qi = __float2int_rz(y);  // truncation toward zero == round half away after the +-0.5
       qi = max(-128, min(127, qi));
@@ -167,7 +181,7 @@ int run_k(const void* k, int64_t b, int64_t l, int64_t h, float* kmean, int8_t* 
   dim3 g1(static_cast<unsigned>(h), chunks, static_cast<unsigned>(b));
   kmean_partial_kernel<T, D><<<g1, 256, 0, st>>>(static_cast<const T*>(k), partial, l, static_cast<int>(h), chunks);
   if (int rc = check_launch("kmean_partial_kernel")) return rc;
-  kmean_final_kernel<<<static_cast<unsigned>(b * h), 128, 0, st>>>(partial, kmean, l, chunks, D);
+  kmean_final_kernel<<<static_cast<unsigned>(b * h), 1024, 0, st>>>(partial, kmean, l, chunks, D);
   if (int rc = check_launch("kmean_final_kernel")) return rc;
   dim3 gk(static_cast<unsigned>(h), nblk, static_cast<unsigned>(b));
   pool_quant_kernel<T, D, 64, true><<<gk, 64 * D / 64, 0, st>>>(static_cast<const T*>(k), kmean, k_i8, k_scale,
