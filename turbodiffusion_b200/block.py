@@ -27,10 +27,10 @@ from .turbo_diffusion_ops import (gelu_quant_cuda, gemm_cuda_bias_gelu, gemm_cud
 #   "fused": bias + GELU (one-MUFU tanh) + quantisation in the up-projection's epilogue: no 16-bit intermediate in HBM; the
 #            epilogue runs on the warps that dequantise (shape A: 0.886 ms vs 0.552 ms for the plain GEMM);
 #   "split": up-projection writes T(acc + bias); one HBM pass applies GELU(tanh) and the 128x128-block quantisation
-#            (tdb200_gelu_quant_int8_block128, 0.285 ms at shape A): exact fp32 GELU, no activation on the GEMM's dequant warps.
-# Measured in the step (profiles/r02_bench_ffn_modes.txt): with the packed one-MUFU activation kernel (0.200 ms at shape A) split
-# is 103.2 ms and fused 104.2 ms per denoise step -> split is the default.
-FFN_ACT_MODE = os.environ.get("TDB200_FFN_ACT", "split")
+#            (tdb200_gelu_quant_int8_block128, 0.200 ms at shape A), no activation on the GEMM's dequant warps.
+# Measured in the step (profiles/r02_bench_ffn_modes.txt), both with packed arithmetic: fused 99.7 ms (up-projection 0.660 ms at shape A),
+# split 102.0 ms (0.492 ms + 0.200 ms) per denoise step -> fused is the default.
+FFN_ACT_MODE = os.environ.get("TDB200_FFN_ACT", "fused")
 
 LINEARS = ("self_attn.q", "self_attn.k", "self_attn.v", "self_attn.o", "cross_attn.q", "cross_attn.k", "cross_attn.v",
            "cross_attn.o", "ffn.0", "ffn.2")

@@ -409,6 +409,20 @@ struct F16Traits<__half> {
   }
 };
 
+// Four scaled values -> four saturated int8 codes (round to nearest even), WITHOUT the XU pipe: cvt.rni.sat.s8.f32 is an F2I on the
+// quarter-rate conversion unit; the 1.5*2^23 magic add rounds to nearest even on the FMA pipe and leaves the two's-complement
+// integer in the low mantissa bits (|v| <= 128 here).  Only the +128 edge needs the explicit clamp (v >= -128 by construction).
+__device__ __forceinline__ uint32_t pack4_s8_rne(float a, float b, float c, float d) {
+  constexpr float kMagic = 12582912.0f;
+  const uint32_t ia = __float_as_uint(__fadd_rn(fminf(a, 127.0f), kMagic));
+  const uint32_t ib = __float_as_uint(__fadd_rn(fminf(b, 127.0f), kMagic));
+  const uint32_t ic = __float_as_uint(__fadd_rn(fminf(c, 127.0f), kMagic));
+  const uint32_t id = __float_as_uint(__fadd_rn(fminf(d, 127.0f), kMagic));
+  const uint32_t lo = __byte_perm(ia, ib, 0x0040);   // byte0 = ia.b0, byte1 = ib.b0
+  const uint32_t hi = __byte_perm(ic, id, 0x0040);
+  return __byte_perm(lo, hi, 0x5410);                // ia.b0 | ib.b0 << 8 | ic.b0 << 16 | id.b0 << 24
+}
+
 // bare MUFU.EX2 (no denormal fix-up code around it)
 __device__ __forceinline__ float fast_exp2(float x) {
   float y;

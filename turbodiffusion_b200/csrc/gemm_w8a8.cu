@@ -422,17 +422,10 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           uint32_t w[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            uint32_t word = 0;
-#pragma unroll
-            for (int b = 0; b < 2; ++b) {
-              const uint32_t y = yw[ch * 8 + j * 2 + b];
-              const float2 v = __fmul2_rn(make_float2(F16Traits<T>::lo(y), F16Traits<T>::hi(y)), r2);
-              int q0, q1;
-              asm("cvt.rni.sat.s8.f32 %0, %1;" : "=r"(q0) : "f"(v.x));
-              asm("cvt.rni.sat.s8.f32 %0, %1;" : "=r"(q1) : "f"(v.y));
-              word |= ((static_cast<uint32_t>(q0) & 0xFFu) | ((static_cast<uint32_t>(q1) & 0xFFu) << 8)) << (16 * b);
-            }
-            w[j] = word;
+            const uint32_t y0 = yw[ch * 8 + j * 2], y1 = yw[ch * 8 + j * 2 + 1];
+            const float2 v0 = __fmul2_rn(make_float2(F16Traits<T>::lo(y0), F16Traits<T>::hi(y0)), r2);
+            const float2 v1 = __fmul2_rn(make_float2(F16Traits<T>::lo(y1), F16Traits<T>::hi(y1)), r2);
+            w[j] = pack4_s8_rne(v0.x, v0.y, v1.x, v1.y);
           }
           *reinterpret_cast<uint4*>(stage + lane * 128 + ((ch ^ (lane & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
         }

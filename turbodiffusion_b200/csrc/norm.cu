@@ -82,7 +82,9 @@ __device__ __forceinline__ void load_params(const float* __restrict__ p, float* 
 // difference (< 1e-6 abs) moves a bf16 result by one ulp in ~1e-4 of the elements, inside the stated RoPE tolerance,
 // and keeps this kernel HBM-bound instead of bound by the ~40-instruction accurate sincosf.
 __device__ __forceinline__ void rope_sincos(float x, float* sn, float* cs) {
-  const float n = rintf(x * 0.15915494309189535f);
+  // round(x / 2pi) by the 1.5*2^23 magic add on the FMA pipe (rintf is an FRND on the conversion unit, which these kernels
+  // already load with sin/cos); exact for |x / 2pi| < 2^22
+  const float n = __fadd_rn(__fmaf_rn(x, 0.15915494309189535f, 12582912.0f), -12582912.0f);
   float r = fmaf(n, -6.2831854820251465f, x);
   r = fmaf(n, 1.7484555e-7f, r);
   *sn = __sinf(r);
@@ -400,11 +402,14 @@ __global__ void __launch_bounds__(256) ln_modulate_quant_tile_kernel(const T* __
     float f[8];
     Chunk<T>::unpack(raw[p], f);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float t = Chunk<T>::round(__fmul_rn(f[j] - mu[p], rs[p]));
-      t = Chunk<T>::round(__fadd_rn(__fmul_rn(t, sc[j]), sh[j]));  // the modulated activation in T, as quant_cuda sees it
-      v[p][j] = ok ? t : 0.f;
-      amax = fmaxf(amax, fabsf(v[p][j]));
+    for (int j = 0; j < 8; j += 2) {
+      // both roundings to T are done on PAIRS (one pack instruction per two values instead of one conversion each)
+      const uint32_t n2 = F16Traits<T>::pack(__fmul_rn(f[j] - mu[p], rs[p]), __fmul_rn(f[j + 1] - mu[p], rs[p]));
+      const uint32_t m2 = F16Traits<T>::pack(__fadd_rn(__fmul_rn(F16Traits<T>::lo(n2), sc[j]), sh[j]),
+                                             __fadd_rn(__fmul_rn(F16Traits<T>::hi(n2), sc[j + 1]), sh[j + 1]));  // the modulated activation in T, as quant_cuda sees it
+      v[p][j] = ok ? F16Traits<T>::lo(m2) : 0.f;
+      v[p][j + 1] = ok ? F16Traits<T>::hi(m2) : 0.f;
+      amax = fmaxf(amax, fmaxf(fabsf(v[p][j]), fabsf(v[p][j + 1])));
     }
   }
   amax = warp_max(amax);
@@ -417,15 +422,8 @@ __global__ void __launch_bounds__(256) ln_modulate_quant_tile_kernel(const T* __
 #pragma unroll
   for (int p = 0; p < 8; ++p) {
     const int64_t row = row0 + p * 16;
-    uint32_t lo = 0, hi = 0;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      int a, b;
-      asm("cvt.rni.sat.s8.f32 %0, %1;" : "=r"(a) : "f"(__fmul_rn(v[p][j], r)));
-      asm("cvt.rni.sat.s8.f32 %0, %1;" : "=r"(b) : "f"(__fmul_rn(v[p][4 + j], r)));
-      lo |= (static_cast<uint32_t>(a) & 0xFFu) << (8 * j);
-      hi |= (static_cast<uint32_t>(b) & 0xFFu) << (8 * j);
-    }
+    const uint32_t lo = pack4_s8_rne(__fmul_rn(v[p][0], r), __fmul_rn(v[p][1], r), __fmul_rn(v[p][2], r), __fmul_rn(v[p][3], r));
+    const uint32_t hi = pack4_s8_rne(__fmul_rn(v[p][4], r), __fmul_rn(v[p][5], r), __fmul_rn(v[p][6], r), __fmul_rn(v[p][7], r));
     if (col_ok && row < m) *reinterpret_cast<uint2*>(q + row * n + col) = make_uint2(lo, hi);
   }
 }

@@ -65,15 +65,8 @@ __global__ void __launch_bounds__(kThreads) quant_int8_block128_kernel(const T* 
 #pragma unroll
   for (int p = 0; p < kPasses; ++p) {
     const int64_t row = row0 + p * kRowsPerPass;
-    uint32_t lo = 0, hi = 0;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      int a, b;
-      asm("cvt.rni.sat.s8.f32 %0, %1;" : "=r"(a) : "f"(__fmul_rn(v[p][j], r)));
-      asm("cvt.rni.sat.s8.f32 %0, %1;" : "=r"(b) : "f"(__fmul_rn(v[p][4 + j], r)));
-      lo |= (static_cast<uint32_t>(a) & 0xFFu) << (8 * j);
-      hi |= (static_cast<uint32_t>(b) & 0xFFu) << (8 * j);
-    }
+    const uint32_t lo = pack4_s8_rne(__fmul_rn(v[p][0], r), __fmul_rn(v[p][1], r), __fmul_rn(v[p][2], r), __fmul_rn(v[p][3], r));
+    const uint32_t hi = pack4_s8_rne(__fmul_rn(v[p][4], r), __fmul_rn(v[p][5], r), __fmul_rn(v[p][6], r), __fmul_rn(v[p][7], r));
     if (col_ok && row < m) *reinterpret_cast<uint2*>(q + row * k + col) = make_uint2(lo, hi);
   }
 }
@@ -137,14 +130,12 @@ __global__ void __launch_bounds__(kThreads) gelu_quant_int8_block128_kernel(cons
 #pragma unroll
   for (int p = 0; p < kPasses; ++p) {
     const int64_t row = row0 + p * kRowsPerPass;
-    uint32_t word[2] = {0u, 0u};
+    uint32_t word[2];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float2 v = __fmul2_rn(make_float2(F16Traits<T>::lo(g[p][j]), F16Traits<T>::hi(g[p][j])), r2);
-      int a, b;
-      asm("cvt.rni.sat.s8.f32 %0, %1;" : "=r"(a) : "f"(v.x));
-      asm("cvt.rni.sat.s8.f32 %0, %1;" : "=r"(b) : "f"(v.y));
-      word[j >> 1] |= ((static_cast<uint32_t>(a) & 0xFFu) | ((static_cast<uint32_t>(b) & 0xFFu) << 8)) << (16 * (j & 1));
+    for (int j = 0; j < 4; j += 2) {
+      const float2 v0 = __fmul2_rn(make_float2(F16Traits<T>::lo(g[p][j]), F16Traits<T>::hi(g[p][j])), r2);
+      const float2 v1 = __fmul2_rn(make_float2(F16Traits<T>::lo(g[p][j + 1]), F16Traits<T>::hi(g[p][j + 1])), r2);
+      word[j >> 1] = pack4_s8_rne(v0.x, v0.y, v1.x, v1.y);
     }
     if (col_ok && row < m) *reinterpret_cast<uint2*>(q + row * k + col) = make_uint2(word[0], word[1]);
   }
