@@ -82,9 +82,7 @@ __device__ __forceinline__ void load_params(const float* __restrict__ p, float* 
 // difference (< 1e-6 abs) moves a bf16 result by one ulp in ~1e-4 of the elements, inside the stated RoPE tolerance,
 // and keeps this kernel HBM-bound instead of bound by the ~40-instruction accurate sincosf.
 __device__ __forceinline__ void rope_sincos(float x, float* sn, float* cs) {
-  // round(x / 2pi) by the 1.5*2^23 magic add on the FMA pipe (rintf is an FRND on the conversion unit, which these kernels
-  // already load with sin/cos); exact for |x / 2pi| < 2^22
-  const float n = __fadd_rn(__fmaf_rn(x, 0.15915494309189535f, 12582912.0f), -12582912.0f);
+  const float n = rintf(x * 0.15915494309189535f);   // (a magic-add rounding on the FMA pipe measured slower here: 72 vs 62 us)
   float r = fmaf(n, -6.2831854820251465f, x);
   r = fmaf(n, 1.7484555e-7f, r);
   *sn = __sinf(r);
