@@ -48,7 +48,7 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-template <typename T>
+template <typename T, bool kPair>
 __global__ void __launch_bounds__(kThreads, 1)
 sla_moments_kernel(const __grid_constant__ CUtensorMap tmap_v, MomParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -57,7 +57,7 @@ sla_moments_kernel(const __grid_constant__ CUtensorMap tmap_v, MomParams p) {
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kNumBars);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int hh = blockIdx.x, split = blockIdx.y, b = blockIdx.z;  // heads (or head pairs) fastest: DRAM page locality of [L, H, D]
-  const bool pair = p.hd == 64;
+  constexpr bool pair = kPair;
   const int head0 = pair ? 2 * hh : hh;                            // first real head of this CTA
   const bool second_ok = !pair || head0 + 1 < p.h;                 // odd head count: the last pair has one real head
   const int64_t row_elems = int64_t(p.h) * p.hd;                   // elements per token row of k / v
@@ -119,43 +119,64 @@ sla_moments_kernel(const __grid_constant__ CUtensorMap tmap_v, MomParams p) {
   } else {
     const int r = warp * 32 + lane;  // key row inside the tile; later: value channel (TMEM lane) / key channel (ksum)
     float ksum_acc = 0.f;
+    // The key rows of tile i+1 are requested before tile i is transformed (16 independent 16-byte loads per thread in flight
+    // under the exponentials), and phi needs ONE exponential per element: e_j is kept in fp32 registers until the row sum is
+    // known.  (Round 1 loaded, waited, and evaluated every exponential twice: 9.8k clk per 128-row tile.)
+    auto load_row = [&](int i, uint4 (&dst)[D / 8]) {
+      const int64_t row = int64_t(split + i * p.splits) * kRowsPerTile + r;
+      const int nload = (i < my_tiles && row < p.l) ? (second_ok ? D / 8 : D / 16) : 0;   // missing second head: zeros
+      const uint4* src = reinterpret_cast<const uint4*>(static_cast<const T*>(p.k) +
+                                                        (int64_t(b) * p.l + (row < p.l ? row : 0)) * row_elems + int64_t(head0) * p.hd);
+#pragma unroll
+      for (int c = 0; c < D / 8; ++c) {
+        dst[c] = make_uint4(0u, 0u, 0u, 0u);
+        if (c < nload) dst[c] = ldg_nc_v4(src + c);
+      }
+    };
+    uint4 cur[D / 8];
+    load_row(0, cur);
     for (int i = 0; i < my_tiles; ++i) {
       const int st = i & 1, tile = split + i * p.splits;
       const int64_t row = int64_t(tile) * kRowsPerTile + r;
+      uint4 nxt[D / 8];
+      load_row(i + 1, nxt);
       uint32_t w[D / 2];
+#pragma unroll
+      for (int c = 0; c < D / 8; ++c) { w[4 * c] = cur[c].x; w[4 * c + 1] = cur[c].y; w[4 * c + 2] = cur[c].z; w[4 * c + 3] = cur[c].w; }
       if (row < p.l) {
-        const uint4* src = reinterpret_cast<const uint4*>(static_cast<const T*>(p.k) + (int64_t(b) * p.l + row) * row_elems + int64_t(head0) * p.hd);
-        const int nload = second_ok ? D / 8 : D / 16;   // the second half belongs to the next (non-existent) head
+        // phi over each segment of the row (one 128-wide segment, or two 64-wide segments for a pair of 64-wide heads)
+        constexpr int kSeg = kPair ? 2 : 1, kWps = (D / 2) / kSeg;   // segments, 32-bit words per segment
 #pragma unroll
-        for (int c = 0; c < D / 8; ++c) {
-          uint4 raw = make_uint4(0u, 0u, 0u, 0u);
-          if (c < nload) raw = ldg_nc_v4(src + c);
-          w[4 * c] = raw.x; w[4 * c + 1] = raw.y; w[4 * c + 2] = raw.z; w[4 * c + 3] = raw.w;
-        }
-        // phi over each `seg`-wide segment of the row (one segment for a 128-wide head, two for a pair of 64-wide heads)
-#pragma unroll
-        for (int sgm = 0; sgm < 2; ++sgm) {
-          if (!pair && sgm == 1) break;
-          const int w0 = pair ? sgm * (D / 4) : 0, w1 = pair ? (sgm + 1) * (D / 4) : D / 2;
+        for (int sgm = 0; sgm < kSeg; ++sgm) {
+          const int w0 = sgm * kWps;
           if (p.feature == 0) {
-            float mx = -INFINITY;
-            for (int q = w0; q < w1; ++q) mx = fmaxf(mx, fmaxf(F16Traits<T>::lo(w[q]), F16Traits<T>::hi(w[q])));
-            const float off = mx * kLog2e;
-            float sa = 0.f, sb = 0.f;
-            for (int q = w0; q < w1; ++q) {
-              sa += fast_exp2(fmaf(F16Traits<T>::lo(w[q]), kLog2e, -off));
-              sb += fast_exp2(fmaf(F16Traits<T>::hi(w[q]), kLog2e, -off));
+            float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+            for (int q = 0; q < kWps; q += 2) {
+              m0 = fmaxf(m0, fmaxf(F16Traits<T>::lo(w[w0 + q]), F16Traits<T>::hi(w[w0 + q])));
+              m1 = fmaxf(m1, fmaxf(F16Traits<T>::lo(w[w0 + q + 1]), F16Traits<T>::hi(w[w0 + q + 1])));
             }
-            const float inv = 1.0f / (sa + sb);
-            for (int q = w0; q < w1; ++q)
-              w[q] = F16Traits<T>::pack(fast_exp2(fmaf(F16Traits<T>::lo(w[q]), kLog2e, -off)) * inv,
-                                       fast_exp2(fmaf(F16Traits<T>::hi(w[q]), kLog2e, -off)) * inv);
+            const float off = fmaxf(m0, m1) * kLog2e;
+            float e[2 * kWps];
+            float sa = 0.f, sb = 0.f, sc4 = 0.f, sd = 0.f;  // independent chains
+#pragma unroll
+            for (int q = 0; q < kWps; q += 2) {
+              e[2 * q] = fast_exp2(fmaf(F16Traits<T>::lo(w[w0 + q]), kLog2e, -off));
+              e[2 * q + 1] = fast_exp2(fmaf(F16Traits<T>::hi(w[w0 + q]), kLog2e, -off));
+              e[2 * q + 2] = fast_exp2(fmaf(F16Traits<T>::lo(w[w0 + q + 1]), kLog2e, -off));
+              e[2 * q + 3] = fast_exp2(fmaf(F16Traits<T>::hi(w[w0 + q + 1]), kLog2e, -off));
+              sa += e[2 * q]; sb += e[2 * q + 1]; sc4 += e[2 * q + 2]; sd += e[2 * q + 3];
+            }
+            const float inv = 1.0f / ((sa + sb) + (sc4 + sd));
+#pragma unroll
+            for (int q = 0; q < kWps; ++q) w[w0 + q] = F16Traits<T>::pack(e[2 * q] * inv, e[2 * q + 1] * inv);
           } else {
-            for (int q = w0; q < w1; ++q) {
-              const float a = F16Traits<T>::lo(w[q]), c = F16Traits<T>::hi(w[q]);
+#pragma unroll
+            for (int q = 0; q < kWps; ++q) {
+              const float a = F16Traits<T>::lo(w[w0 + q]), c = F16Traits<T>::hi(w[w0 + q]);
               const float fa = p.feature == 1 ? (a > 0.f ? a + 1.0f : fast_exp2(a * kLog2e)) : fmaxf(a, 0.f);
               const float fc = p.feature == 1 ? (c > 0.f ? c + 1.0f : fast_exp2(c * kLog2e)) : fmaxf(c, 0.f);
-              w[q] = F16Traits<T>::pack(fa, fc);
+              w[w0 + q] = F16Traits<T>::pack(fa, fc);
             }
           }
         }
@@ -167,6 +188,8 @@ sla_moments_kernel(const __grid_constant__ CUtensorMap tmap_v, MomParams p) {
 #pragma unroll
         for (int q = 0; q < D / 2; ++q) w[q] = 0u;
       }
+#pragma unroll
+      for (int c = 0; c < D / 8; ++c) cur[c] = nxt[c];
       // stage free? (the MMA that read it two tiles ago has retired)
       mbar_wait(&bars[kStageEmpty + st], ((i >> 1) & 1) ^ 1);
       uint8_t* sphi = smem + kOffPhi + st * kOperandBytes;
@@ -277,17 +300,19 @@ static int moments_impl(const void* k, const void* v, int dtype, int64_t b, int6
   p.splits = splits;
   dim3 grid(static_cast<unsigned>(units), splits, static_cast<unsigned>(b));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-#define TDB_MOM(T)                                                                                                  \
+#define TDB_MOM2(T, PAIR)                                                                                          \
   do {                                                                                                              \
     static bool attr_done[64] = {false};                                                                            \
-    if (int rc = set_max_dynamic_smem_once(reinterpret_cast<const void*>(sla_moments_kernel<T>), kSmemBytes, attr_done, \
+    if (int rc = set_max_dynamic_smem_once(reinterpret_cast<const void*>(sla_moments_kernel<T, PAIR>), kSmemBytes, attr_done, \
                                            "cudaFuncSetAttribute(sla_moments)"))                                   \
       return rc;                                                                                                    \
-    sla_moments_kernel<T><<<grid, kThreads, kSmemBytes, st>>>(tv, p);                                               \
+    sla_moments_kernel<T, PAIR><<<grid, kThreads, kSmemBytes, st>>>(tv, p);                                         \
     return check_launch("sla_moments_kernel");                                                                      \
   } while (0)
+#define TDB_MOM(T) do { if (d == 64) { TDB_MOM2(T, true); } else { TDB_MOM2(T, false); } } while (0)
   if (dtype == TDB200_DTYPE_BF16) TDB_MOM(__nv_bfloat16);
   if (dtype == TDB200_DTYPE_FP16) TDB_MOM(__half);
+#undef TDB_MOM2
 #undef TDB_MOM
   return fail(TDB200_ERR_UNSUPPORTED, "sla_linear_moments: dtype tag %d", dtype);
 }
