@@ -174,6 +174,23 @@ int tdb200_sla_attn_fwd(const int8_t* q_i8, const float* q_scale, const int8_t* 
                         const void* v, const void* q, int dtype, const int32_t* lut, int64_t topk, const void* kvw,
                         const float* ksum, const float* proj_b, void* out, int64_t b, int64_t l, int64_t lk,
                         int64_t h, int64_t d, float sm_scale, void* stream);
+/* Sequence-parallel form of the key half of tdb200_sla_quant_qk (reference: the context-parallel attention of
+ * rcm/utils/a2a_cp.py:66-182 exchanges 16-bit K; here each rank quantises its own key rows and the INT8 tensor travels).
+ *   tdb200_sla_kmean_partial  partial [b,h,ceil(l/128),d] fp32 = column sums of each 128-row chunk of k [b,l,h,d];
+ *   tdb200_sla_kmean_final    kmean [b,h,d] = (fixed-order sum of `chunks` partials) / l_total  -- the reduction
+ *                             tdb200_sla_quant_qk runs, so gathering every rank's partials reproduces its mean bit for bit;
+ *   tdb200_sla_quant_k_seq    smoothed Sage INT8 of k's rows: k_i8 in the INPUT layout [b,l,h,d], k_scale [b,h,ceil(l/64)],
+ *                             k_pool [b,h,ceil(l/64),d];
+ *   tdb200_sla_attn_fwd_kseq  tdb200_sla_attn_fwd with k_i8 in that [b,lk,h,d] layout. */
+int tdb200_sla_kmean_partial(const void* k, int dtype, int64_t b, int64_t l, int64_t h, int64_t d, float* partial, void* stream);
+int tdb200_sla_kmean_final(const float* partial, int64_t b, int64_t h, int64_t chunks, int64_t d, int64_t l_total, float* kmean,
+                           void* stream);
+int tdb200_sla_quant_k_seq(const void* k, const float* kmean, int dtype, int64_t b, int64_t l, int64_t h, int64_t d,
+                           int8_t* k_i8, float* k_scale, void* k_pool, void* stream);
+int tdb200_sla_attn_fwd_kseq(const int8_t* q_i8, const float* q_scale, const int8_t* k_i8, const float* k_scale,
+                             const void* v, const void* q, int dtype, const int32_t* lut, int64_t topk, const void* kvw,
+                             const float* ksum, const float* proj_b, void* out, int64_t b, int64_t l, int64_t lk,
+                             int64_t h, int64_t d, float sm_scale, void* stream);
 /* The non-quantised SLA path (reference: Triton _attn_fwd, turbodiffusion/SLA/kernel.py:33-82, used by SparseLinearAttention
  * when --attention_type sla): the same fused kernel with Q.K^T as a 16-bit tensor-core product on the un-quantised q, k
  * [b,l,h,d] (fp32 scores, exp2 softmax, P rounded to T before P.V, :60-73); no q/k scales, no key smoothing. */

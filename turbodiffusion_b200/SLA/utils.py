@@ -18,7 +18,7 @@ def get_cuda_arch(device_index):
 
 class QKPrep:
     """Outputs of tdb200_sla_quant_qk for q,k in the module layout [B, L, H, D]."""
-    __slots__ = ("kmean", "q_i8", "q_scale", "k_i8", "k_scale", "q_pool", "k_pool", "mblk", "nblk")
+    __slots__ = ("kmean", "q_i8", "q_scale", "k_i8", "k_scale", "q_pool", "k_pool", "mblk", "nblk", "k_seq_major")
 
 
 def quant_qk(q: torch.Tensor, k: torch.Tensor, lk: int = None) -> QKPrep:
@@ -75,6 +75,42 @@ def quant_k_into(o: QKPrep, k: torch.Tensor, lk: int) -> QKPrep:
     check(lib().tdb200_sla_quant_qk(None, ptr(k), DTYPE_TAG[k.dtype], b, lk, lk, h, d, ptr(o.kmean), None, None, ptr(o.k_i8),
                                     ptr(o.k_scale), None, ptr(o.k_pool), stream_ptr(dev)), "sla_quant_qk", launches=3)
     return o
+
+
+def kmean_partials(k: torch.Tensor) -> torch.Tensor:
+    """Column sums of each 128-row chunk of k [B, rows, H, D] -> [B, H, ceil(rows/128), D] fp32: stage one of the key mean
+    (the partials tdb200_sla_quant_qk forms internally; a sequence-parallel rank computes those of its own rows)."""
+    require_cuda(k)
+    b, rows, h, d = k.shape
+    out = torch.empty(b, h, cdiv(rows, 128), d, dtype=torch.float32, device=k.device)
+    check(lib().tdb200_sla_kmean_partial(ptr(k), DTYPE_TAG[k.dtype], b, rows, h, d, ptr(out), stream_ptr(k.device)),
+          "sla_kmean_partial")
+    return out
+
+
+def kmean_from_partials(partials: torch.Tensor, l_total: int) -> torch.Tensor:
+    """Stage two: partials [B, H, chunks, D] fp32 (contiguous, in global chunk order) -> kmean [B, H, D] fp32."""
+    require_cuda(partials)
+    b, h, chunks, d = partials.shape
+    assert partials.is_contiguous() and partials.dtype == torch.float32
+    out = torch.empty(b, h, d, dtype=torch.float32, device=partials.device)
+    check(lib().tdb200_sla_kmean_final(ptr(partials), b, h, chunks, d, l_total, ptr(out), stream_ptr(partials.device)),
+          "sla_kmean_final")
+    return out
+
+
+def quant_k_seq(k: torch.Tensor, kmean: torch.Tensor, k_i8=None):
+    """Smoothed Sage INT8 of the rows of k [B, rows, H, D] against a given key mean: (k_i8 [B, rows, H, D] int8 -- the input
+    layout --, k_scale [B, H, ceil(rows/64)] fp32, k_pool [B, H, ceil(rows/64), D])."""
+    require_cuda(k, kmean)
+    b, rows, h, d = k.shape
+    nb = cdiv(rows, 64)
+    k_i8 = torch.empty(b, rows, h, d, dtype=torch.int8, device=k.device) if k_i8 is None else k_i8
+    k_scale = torch.empty(b, h, nb, dtype=torch.float32, device=k.device)
+    k_pool = torch.empty(b, h, nb, d, dtype=k.dtype, device=k.device)
+    check(lib().tdb200_sla_quant_k_seq(ptr(k), ptr(kmean), DTYPE_TAG[k.dtype], b, rows, h, d, ptr(k_i8), ptr(k_scale),
+                                       ptr(k_pool), stream_ptr(k.device)), "sla_quant_k_seq")
+    return k_i8, k_scale, k_pool
 
 
 def block_map_from_pools(q_pool: torch.Tensor, k_pool: torch.Tensor, topk: int):

@@ -161,7 +161,7 @@ sla_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q8, const __grid_co
           tma_load_4d(smem + kOffK8 + st * kK8Bytes, &tmap_k8, &bars[kBarKFull + st], 0, hh, blk * BLKK, b);
           tma_load_4d(smem + kOffK8 + st * kK8Bytes + kK8Bytes / 2, &tmap_k8, &bars[kBarKFull + st], 64, hh, blk * BLKK, b);
         } else {
-          tma_load_4d(smem + kOffK8 + st * kK8Bytes, &tmap_k8, &bars[kBarKFull + st], 0, blk * BLKK, bh, 0);
+          tma_load_4d(smem + kOffK8 + st * kK8Bytes, &tmap_k8, &bars[kBarKFull + st], 0, blk * BLKK, hh, b);
         }
         mbar_wait(&bars[kBarVEmpty + st], ph);
         mbar_expect_tx(&bars[kBarVFull + st], kVBytes);
@@ -529,7 +529,8 @@ extern "C" int tdb200_debug_set_attn_trace(long long* trace_or_null) {
 template <bool kQK16>
 static int launch_v1(const void* q_op, const float* q_scale, const void* k_op, const float* k_scale, const void* v, const void* q,
                      int dtype, const int32_t* lut, int64_t topk, const void* kvw, const float* ksum, const float* proj_b,
-                     void* out, int64_t b, int64_t l, int64_t lk, int64_t h, int64_t d, float sm_scale, void* stream) {
+                     void* out, int64_t b, int64_t l, int64_t lk, int64_t h, int64_t d, float sm_scale, void* stream,
+                     bool k_seq_major = false) {
   using namespace tdb;
   using L = Lay<kQK16>;
   if (!q_op || !k_op || !v || !q || !lut || !kvw || !ksum || !proj_b || !out || (!kQK16 && (!q_scale || !k_scale)))
@@ -564,8 +565,9 @@ static int launch_v1(const void* q_op, const float* q_scale, const void* k_op, c
       if (int rc = make_tmap_4d(&tq, q_op, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, dims, str, box)) return rc;
     }
     {
-      const uint64_t dims[4] = {uint64_t(d), uint64_t(lk), uint64_t(b * h), 1};
-      const uint64_t str[3] = {uint64_t(d), uint64_t(lk * d), uint64_t(b * h * lk * d)};
+      // INT8 K: head-major [b, h, lk, d] (tdb200_sla_quant_qk) or, for sequence-parallel callers, the gathered [b, lk, h, d]
+      const uint64_t dims[4] = {uint64_t(d), uint64_t(lk), uint64_t(h), uint64_t(b)};
+      const uint64_t str[3] = {uint64_t(k_seq_major ? h * d : d), uint64_t(k_seq_major ? d : lk * d), uint64_t(h * lk * d)};
       const uint32_t box[4] = {D, BLKK, 1, 1};
       if (int rc = make_tmap_4d(&tk, k_op, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, dims, str, box)) return rc;
     }
@@ -625,6 +627,15 @@ extern "C" int tdb200_sla_attn_fwd(const int8_t* q_i8, const float* q_scale, con
                                    const void* kvw, const float* ksum, const float* proj_b, void* out, int64_t b,
                                    int64_t l, int64_t lk, int64_t h, int64_t d, float sm_scale, void* stream) {
   return launch_v1<false>(q_i8, q_scale, k_i8, k_scale, v, q, dtype, lut, topk, kvw, ksum, proj_b, out, b, l, lk, h, d, sm_scale, stream);
+}
+
+// the same kernel reading INT8 K in the [b, lk, h, d] layout (tdb200_sla_quant_k_seq; what sequence-parallel ranks all-gather)
+extern "C" int tdb200_sla_attn_fwd_kseq(const int8_t* q_i8, const float* q_scale, const int8_t* k_i8, const float* k_scale,
+                                        const void* v, const void* q, int dtype, const int32_t* lut, int64_t topk,
+                                        const void* kvw, const float* ksum, const float* proj_b, void* out, int64_t b,
+                                        int64_t l, int64_t lk, int64_t h, int64_t d, float sm_scale, void* stream) {
+  return launch_v1<false>(q_i8, q_scale, k_i8, k_scale, v, q, dtype, lut, topk, kvw, ksum, proj_b, out, b, l, lk, h, d, sm_scale, stream,
+                          true);
 }
 
 extern "C" int tdb200_sla_attn_fwd_qk16(const void* q, const void* k, const void* v, int dtype, const int32_t* lut, int64_t topk,

@@ -16,7 +16,8 @@
 namespace {
 using namespace tdb;
 
-constexpr int kMeanRows = 256;  // rows per partial in the key-mean pass
+constexpr int kMeanRows = 128;  // rows per partial in the key-mean pass (= the sequence-parallel shard alignment, so a rank's
+                                // partials are exactly the single-GPU partials of its rows)
 
 // ---- stage 1 of the key mean: partial column sums over kMeanRows rows ---------------------------------------
 template <typename T, int D>
@@ -79,7 +80,8 @@ template <typename T, int D, int ROWS, bool kSubMean>
 __global__ void __launch_bounds__(ROWS* D / 64) pool_quant_kernel(const T* __restrict__ x,
                                                                    const float* __restrict__ kmean,
                                                                    int8_t* __restrict__ x_i8, float* __restrict__ scale,
-                                                                   T* __restrict__ pool, int64_t l, int h, int nblk) {
+                                                                   T* __restrict__ pool, int64_t l, int h, int nblk,
+                                                                   int64_t out_row_stride, int64_t out_head_stride) {
   constexpr int THREADS = ROWS * D / 64;
   constexpr int CPR = D / 8;
   constexpr int RPP = THREADS / CPR;
@@ -157,7 +159,8 @@ __global__ void __launch_bounds__(ROWS* D / 64) pool_quant_kernel(const T* __res
       else
         hi |= (static_cast<uint32_t>(qi) & 0xFFu) << (8 * (j - 4));
     }
-    if (row < l) *reinterpret_cast<uint2*>(x_i8 + (bh * l + row) * D + c * 8) = make_uint2(lo, hi);
+    if (row < l)
+      *reinterpret_cast<uint2*>(x_i8 + int64_t(b) * h * l * D + hh * out_head_stride + row * out_row_stride + c * 8) = make_uint2(lo, hi);
   }
 }
 
@@ -166,27 +169,41 @@ int run_q(const void* q, int64_t b, int64_t lq, int64_t h, int8_t* q_i8, float* 
   const int mblk = static_cast<int>(cdiv64(lq, 128));
   dim3 gq(static_cast<unsigned>(h), mblk, static_cast<unsigned>(b));
   pool_quant_kernel<T, D, 128, false><<<gq, 128 * D / 64, 0, st>>>(static_cast<const T*>(q), nullptr, q_i8, q_scale,
-                                                                   static_cast<T*>(q_pool), lq, static_cast<int>(h), mblk);
+                                                                   static_cast<T*>(q_pool), lq, static_cast<int>(h), mblk, D, lq * D);
   return check_launch("pool_quant_kernel<q>");
+}
+
+template <typename T, int D>
+int run_kmean_partial(const void* k, int64_t b, int64_t l, int64_t h, float* partial, cudaStream_t st) {
+  const int chunks = static_cast<int>(cdiv64(l, kMeanRows));
+  dim3 g1(static_cast<unsigned>(h), chunks, static_cast<unsigned>(b));
+  kmean_partial_kernel<T, D><<<g1, 256, 0, st>>>(static_cast<const T*>(k), partial, l, static_cast<int>(h), chunks);
+  return check_launch("kmean_partial_kernel");
+}
+
+// seq_major: k_i8 keeps the input's [b, l, h, d] layout (what a sequence-parallel rank all-gathers) instead of [b, h, l, d]
+template <typename T, int D>
+int run_k_quant(const void* k, int64_t b, int64_t l, int64_t h, const float* kmean, int8_t* k_i8, float* k_scale, void* k_pool,
+                bool seq_major, cudaStream_t st) {
+  const int nblk = static_cast<int>(cdiv64(l, 64));
+  dim3 gk(static_cast<unsigned>(h), nblk, static_cast<unsigned>(b));
+  pool_quant_kernel<T, D, 64, true><<<gk, 64 * D / 64, 0, st>>>(static_cast<const T*>(k), kmean, k_i8, k_scale,
+                                                                static_cast<T*>(k_pool), l, static_cast<int>(h), nblk,
+                                                                seq_major ? h * D : D, seq_major ? D : l * D);
+  return check_launch("pool_quant_kernel<k>");
 }
 
 template <typename T, int D>
 int run_k(const void* k, int64_t b, int64_t l, int64_t h, float* kmean, int8_t* k_i8, float* k_scale, void* k_pool,
           cudaStream_t st) {
-  const int nblk = static_cast<int>(cdiv64(l, 64));
   const int chunks = static_cast<int>(cdiv64(l, kMeanRows));
   // scratch for the partial column sums: chunks*D floats per head.  They fit in the not-yet-written k_i8 buffer (l*D bytes
-  // per head) whenever 4*chunks <= l, i.e. l >= 4; a single chunk (l <= 256) reduces in place in the kmean output itself.
+  // per head) whenever 4*chunks <= l, i.e. l >= 4; a single chunk (l <= 128) reduces in place in the kmean output itself.
   float* partial = chunks == 1 ? kmean : reinterpret_cast<float*>(k_i8);
-  dim3 g1(static_cast<unsigned>(h), chunks, static_cast<unsigned>(b));
-  kmean_partial_kernel<T, D><<<g1, 256, 0, st>>>(static_cast<const T*>(k), partial, l, static_cast<int>(h), chunks);
-  if (int rc = check_launch("kmean_partial_kernel")) return rc;
+  if (int rc = run_kmean_partial<T, D>(k, b, l, h, partial, st)) return rc;
   kmean_final_kernel<<<static_cast<unsigned>(b * h), 1024, 0, st>>>(partial, kmean, l, chunks, D);
   if (int rc = check_launch("kmean_final_kernel")) return rc;
-  dim3 gk(static_cast<unsigned>(h), nblk, static_cast<unsigned>(b));
-  pool_quant_kernel<T, D, 64, true><<<gk, 64 * D / 64, 0, st>>>(static_cast<const T*>(k), kmean, k_i8, k_scale,
-                                                                static_cast<T*>(k_pool), l, static_cast<int>(h), nblk);
-  return check_launch("pool_quant_kernel<k>");
+  return run_k_quant<T, D>(k, b, l, h, kmean, k_i8, k_scale, k_pool, false, st);
 }
 
 template <typename T, int D>
@@ -225,4 +242,56 @@ extern "C" int tdb200_sla_quant_qk(const void* q, const void* k, int dtype, int6
   }
 #undef TDB_RUN
   return fail(TDB200_ERR_UNSUPPORTED, "sla_quant_qk: dtype tag %d", dtype);
+}
+
+// ---- the key half split in three, for sequence-parallel ranks (dist.py): each rank reduces ITS rows to 128-row partial sums,
+// the partials are all-gathered (they are exactly the single-GPU partials, so the mean is bit-identical), every rank finishes
+// the mean and quantises / pools only its own key rows; INT8 K travels in the [b, l, h, d] layout it is gathered in. -------------
+extern "C" int tdb200_sla_kmean_partial(const void* k, int dtype, int64_t b, int64_t l, int64_t h, int64_t d, float* partial,
+                                        void* stream) {
+  using namespace tdb;
+  if (!k || !partial) return fail(TDB200_ERR_INVALID_ARG, "sla_kmean_partial: null pointer");
+  if (b <= 0 || l <= 0 || h <= 0) return fail(TDB200_ERR_INVALID_ARG, "sla_kmean_partial: bad shape");
+  if (d != 64 && d != 128) return fail(TDB200_ERR_UNSUPPORTED, "sla_kmean_partial: head dim %lld (64 or 128)", (long long)d);
+  if (h > 65535 || b > 65535 || cdiv64(l, kMeanRows) > 65535) return fail(TDB200_ERR_UNSUPPORTED, "sla_kmean_partial: dimension too large");
+  if (!aligned16(k)) return fail(TDB200_ERR_INVALID_ARG, "sla_kmean_partial: k must be 16-byte aligned");
+  if (int rc = require_sm100()) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == TDB200_DTYPE_BF16) return d == 128 ? run_kmean_partial<__nv_bfloat16, 128>(k, b, l, h, partial, st) : run_kmean_partial<__nv_bfloat16, 64>(k, b, l, h, partial, st);
+  if (dtype == TDB200_DTYPE_FP16) return d == 128 ? run_kmean_partial<__half, 128>(k, b, l, h, partial, st) : run_kmean_partial<__half, 64>(k, b, l, h, partial, st);
+  return fail(TDB200_ERR_UNSUPPORTED, "sla_kmean_partial: dtype tag %d", dtype);
+}
+
+extern "C" int tdb200_sla_kmean_final(const float* partial, int64_t b, int64_t h, int64_t chunks, int64_t d, int64_t l_total,
+                                      float* kmean, void* stream) {
+  using namespace tdb;
+  if (!partial || !kmean) return fail(TDB200_ERR_INVALID_ARG, "sla_kmean_final: null pointer");
+  if (b <= 0 || h <= 0 || chunks <= 0 || l_total <= 0) return fail(TDB200_ERR_INVALID_ARG, "sla_kmean_final: bad shape");
+  if (d != 64 && d != 128) return fail(TDB200_ERR_UNSUPPORTED, "sla_kmean_final: head dim %lld (64 or 128)", (long long)d);
+  if (int rc = require_sm100()) return rc;
+  kmean_final_kernel<<<static_cast<unsigned>(b * h), 1024, 0, static_cast<cudaStream_t>(stream)>>>(partial, kmean, l_total,
+                                                                                                  static_cast<int>(chunks), static_cast<int>(d));
+  return check_launch("kmean_final_kernel");
+}
+
+extern "C" int tdb200_sla_quant_k_seq(const void* k, const float* kmean, int dtype, int64_t b, int64_t l, int64_t h, int64_t d,
+                                      int8_t* k_i8, float* k_scale, void* k_pool, void* stream) {
+  using namespace tdb;
+  if (!k || !kmean || !k_i8 || !k_scale || !k_pool) return fail(TDB200_ERR_INVALID_ARG, "sla_quant_k_seq: null pointer");
+  if (b <= 0 || l <= 0 || h <= 0) return fail(TDB200_ERR_INVALID_ARG, "sla_quant_k_seq: bad shape");
+  if (d != 64 && d != 128) return fail(TDB200_ERR_UNSUPPORTED, "sla_quant_k_seq: head dim %lld (64 or 128)", (long long)d);
+  if (h > 65535 || b > 65535 || cdiv64(l, 64) > 65535) return fail(TDB200_ERR_UNSUPPORTED, "sla_quant_k_seq: dimension too large");
+  if (!aligned16(k) || !aligned16(k_i8)) return fail(TDB200_ERR_INVALID_ARG, "sla_quant_k_seq: buffers must be 16-byte aligned");
+  if (int rc = require_sm100()) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define TDB_RUN(T, D) return run_k_quant<T, D>(k, b, l, h, kmean, k_i8, k_scale, k_pool, true, st)
+  if (dtype == TDB200_DTYPE_BF16) {
+    if (d == 128) TDB_RUN(__nv_bfloat16, 128);
+    TDB_RUN(__nv_bfloat16, 64);
+  } else if (dtype == TDB200_DTYPE_FP16) {
+    if (d == 128) TDB_RUN(__half, 128);
+    TDB_RUN(__half, 64);
+  }
+#undef TDB_RUN
+  return fail(TDB200_ERR_UNSUPPORTED, "sla_quant_k_seq: dtype tag %d", dtype);
 }
