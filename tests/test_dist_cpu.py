@@ -57,6 +57,47 @@ class OraclePrims:
         return (o_s + o_l).to(q.dtype).transpose(1, 2).contiguous()
 
 
+class OraclePrimsI8(OraclePrims):
+    """The INT8-K exchange primitives from the oracle: 128-row partial sums, global mean, per-rank smoothing / Sage INT8 /
+    pooling of the rank's own key rows, and the Sage-emulation attention over the gathered INT8 K."""
+    int8_k = True
+
+    def prepare_q(self, q):
+        return None
+
+    def k_partials(self, k):
+        _, rows, h, d = k.shape
+        pad = (-rows) % 128
+        kf = torch.nn.functional.pad(k[0].float(), (0, 0, 0, 0, 0, pad))               # [rows_p, H, D]
+        return kf.view(-1, 128, h, d).sum(1).permute(1, 0, 2).contiguous().unsqueeze(0)   # [1, H, chunks, D]
+
+    def k_mean(self, partials, l_total):
+        return partials.sum(2) / l_total
+
+    def k_quant(self, k, kmean, out=None):
+        O = self.O
+        kh = k.transpose(1, 2)
+        arg = kh - kmean.to(k.dtype)[:, :, None, :]                                   # T(k - T(mean)), utils.py:56
+        k_i8, k_s = O.sage_quant_blocks(arg, 64)
+        return k_i8.transpose(1, 2).contiguous(), k_s, O.mean_pool(arg, 64)
+
+    def attention_i8(self, q, qprep, k_i8_full, k_scale, k_pool, kmean, v_full, lk, kv, ksum):
+        O = self.O
+        qh = q.transpose(1, 2).contiguous()
+        vh = v_full[:, :lk].transpose(1, 2).contiguous()
+        k8 = k_i8_full[:, :lk].transpose(1, 2).contiguous()
+        scores = (O.mean_pool(qh, 128).float() @ k_pool.float().transpose(-1, -2)).to(q.dtype)
+        nblk = scores.shape[-1]
+        _, lut = O.select_topk(scores, min(nblk, int(self.topk * nblk)))
+        q_i8, q_s = O.sage_quant_blocks(qh, 128)
+        o_s = O.sparse_attention(qh, k8, vh, lut, 128, 64, p_dtype=q.dtype, q_i8=q_i8, q_s=q_s, k_i8=k8, k_s=k_scale)
+        pq = torch.softmax(qh.float(), -1).to(q.dtype).float()
+        num = pq @ kv.transpose(-1, -2)
+        den = 1e-5 + (pq * ksum[:, :, None, :]).sum(-1, keepdim=True)
+        o_l = (num / den) @ self.w.float().t() + self.b.float()
+        return (o_s + o_l).to(q.dtype).transpose(1, 2).contiguous()
+
+
 def _worker(rank, world, port, l, h, d, topk, out_path, mode="allgather"):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -77,13 +118,16 @@ def _worker(rank, world, port, l, h, d, topk, out_path, mode="allgather"):
                 return O.sla_forward(qf, kf, vf, w, b, topk, mode="exact")
         attn = UlyssesAttention(sp, Prims) if h % world == 0 else UnevenUlyssesAttention(sp, Prims, h)
         assert attn.q_first
+    elif mode == "allgather_i8":
+        attn = SPAttention(sp, OraclePrimsI8(O, w, b, topk))
+        assert attn._use_int8(k)
     else:
         attn = SPAttention(sp, OraclePrims(O, w, b, topk))
     sl = slice(sp.row_begin, sp.row_end)
     out_local = attn(q[:, sl].contiguous(), k[:, sl].contiguous(), v[:, sl].contiguous())
     full = sp.gather_rows(out_local[0].reshape(sp.local_rows, h * d))
     if rank == 0:
-        ref = O.sla_forward(q, k, v, w, b, topk, mode="exact")[0].reshape(l, h * d)
+        ref = O.sla_forward(q, k, v, w, b, topk, mode="sage" if mode == "allgather_i8" else "exact")[0].reshape(l, h * d)
         torch.save({"stats": O.stats(full, ref), "rows": [sp.row_begin, sp.row_end]}, out_path)
     dist.barrier()
     dist.destroy_process_group()
@@ -99,6 +143,21 @@ def test_sequence_parallel_attention_gloo_world2(tmp_path, l):
     mp.spawn(_worker, args=(2, port, l, 2, 64, 0.3, out), nprocs=2, join=True)
     res = torch.load(out)
     assert res["stats"]["rel_l2"] < 5e-3, res  # only bf16 output rounding differs from the single-process oracle
+
+
+@pytest.mark.parametrize("l,world", [(600, 2), (1000, 3)])
+def test_int8_k_exchange_gloo(tmp_path, l, world):
+    """INT8-K mode: partial-sum all-gather -> global key mean -> per-rank Sage quantisation -> gathered INT8 K / scales / pooled
+    means reassembled in global block order (uneven last rank; 3 ranks: rows_pad = 384, last rank 232 rows) equals the
+    single-process Sage emulation up to the summation order of the key mean."""
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    out = str(tmp_path / "sp8.pt")
+    mp.spawn(_worker, args=(world, port, l, 2, 128, 0.3, out, "allgather_i8"), nprocs=world, join=True)
+    res = torch.load(out)
+    assert res["stats"]["rel_l2"] < 5e-3, res
 
 
 @pytest.mark.parametrize("l", [600, 1000])

@@ -404,3 +404,57 @@ def test_mean_pool_block_sizes(cuda):
         got = mean_pool(x.to(cuda), blk).cpu()
         ref = O.mean_pool(x, blk)
         assert (got.float() - ref.float()).abs().max() <= 2.0 ** -6 * ref.float().abs().max()
+
+
+@pytest.mark.parametrize("l,h,d,shards", [(1000, 3, 128, (384, 384, 232)), (690, 2, 128, (384, 306)), (1000, 2, 64, (512, 488))])
+def test_split_key_prep_equals_the_fused_one(cuda, l, h, d, shards):
+    """The sequence-parallel form of the key half (dist.py): per-shard 128-row partial sums -> concatenated -> kmean_final, then
+    each shard quantised on its own with the INT8 codes left in the [B, L, H, D] layout, reproduces tdb200_sla_quant_qk's
+    key mean, codes, scales and pooled means BIT FOR BIT (shard boundaries are multiples of 128 rows)."""
+    from turbodiffusion_b200.SLA.utils import QKPrep, kmean_from_partials, kmean_partials, quant_k_into, quant_k_seq
+    assert sum(shards) == l
+    _, k, _ = _qkv(1, l, h, d, seed=31)
+    k = k.to(cuda)
+    ref = quant_k_into(QKPrep(), k, l)
+    parts, row = [], 0
+    for n in shards:
+        parts.append(kmean_partials(k[:, row:row + n].contiguous()))
+        row += n
+    partials = torch.cat(parts, dim=2).contiguous()
+    assert partials.shape[2] == (l + 127) // 128
+    kmean = kmean_from_partials(partials, l)
+    assert torch.equal(kmean, ref.kmean)
+    codes, scales, pools, row = [], [], [], 0
+    for n in shards:
+        c, s, p = quant_k_seq(k[:, row:row + n].contiguous(), kmean)
+        assert c.shape == (1, n, h, d)
+        codes.append(c), scales.append(s), pools.append(p)
+        row += n
+    assert torch.equal(torch.cat(codes, 1).transpose(1, 2), ref.k_i8)
+    assert torch.equal(torch.cat(scales, 2), ref.k_scale)
+    assert torch.equal(torch.cat(pools, 2), ref.k_pool)
+
+
+def test_attention_reads_sequence_major_int8_keys(cuda):
+    """tdb200_sla_attn_fwd_kseq (INT8 K in the gathered [B, Lk, H, D] layout, key rows padded past lk) == tdb200_sla_attn_fwd."""
+    from turbodiffusion_b200.SLA.core import attn_fwd, linear_moments
+    from turbodiffusion_b200.SLA.utils import block_map_from_pools, quant_qk
+    b, l, h, d = 1, 1000, 3, 128
+    q, k, v = (t.to(cuda) for t in _qkv(b, l, h, d, seed=32))
+    prep = quant_qk(q, k)
+    topk = 5
+    _, lut = block_map_from_pools(prep.q_pool, prep.k_pool, topk)
+    kv, ksum = linear_moments(k, v)
+    g = torch.Generator().manual_seed(3)
+    w = (torch.randn(d, d, generator=g) * 0.05).to(cuda)
+    pb = (torch.randn(d, generator=g) * 0.05).to(cuda)
+    kvw = torch.matmul(w, kv).to(q.dtype).contiguous()
+    ref = attn_fwd(prep, v, q, lut, topk, kvw, ksum, pb, d ** -0.5)
+    pad = 152                                                  # the gathered slab carries zero rows past lk
+    k_seq = torch.zeros(b, l + pad, h, d, dtype=torch.int8, device=cuda)
+    k_seq[:, :l] = prep.k_i8.transpose(1, 2)
+    v_pad = torch.zeros(b, l + pad, h, d, dtype=v.dtype, device=cuda)
+    v_pad[:, :l] = v
+    prep.k_i8, prep.k_seq_major = k_seq, True
+    got = attn_fwd(prep, v_pad, q, lut, topk, kvw, ksum, pb, d ** -0.5, lk=l)
+    assert torch.equal(got, ref)

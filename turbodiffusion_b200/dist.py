@@ -3,11 +3,13 @@
 Every GEMM / norm / modulation / RoPE / FFN in the block is row-independent, so rank r simply owns the token rows
 [row_begin, row_end).  Only self-attention needs an exchange (SURVEY 8e / BASELINE north star):
 
-    1. all-gather of the local K and V slabs (16-bit, [rows, H, D]) into one [L_pad, H, D] slab per tensor;
+    1. all-gather of the local V slab (16-bit, [rows, H, D]) and of the local K rows -- as INT8 (Sage-quantised by the owning
+       rank against the global key mean, whose 128-row partial sums are all-gathered first) plus per-block scales and pooled
+       means, or as the 16-bit slab for the shapes the INT8 kernel does not serve -- into one [L_pad, H, D] slab per tensor;
     2. all-reduce (sum) of the linear-attention moments  phi(K)^T V  [H,D,D]  and  sum phi(K)  [H,D], which
        tdb200_sla_linear_moments accumulates over the LOCAL rows only;
-    3. everything else (key mean, INT8 K, block map over all key blocks, fused attention over the gathered K/V) is computed
-       locally for this rank's query rows.
+    3. the block map over all key blocks and the fused attention over the gathered K/V run locally for this rank's query rows
+       (with the 16-bit K exchange also the key mean / INT8 / pooling of the WHOLE key sequence, repeated on every rank).
 
 Shard boundaries are multiples of 128 rows, so 128x128 quant blocks, 128-row query blocks and 64-row key blocks never
 straddle ranks and the result equals the single-GPU computation block for block.  Only the last rank may be short; the
@@ -24,6 +26,7 @@ the K-side preparation of the full sequence; `SequenceParallel.install(mode="aut
 """
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import torch
@@ -44,10 +47,17 @@ def shard_rows(total_rows: int, world: int, rank: int, align: int = 128):
 
 
 class GpuPrimitives:
-    """The C-ABI kernels (default).  The CPU test injects oracle implementations with the same signatures."""
+    """The C-ABI kernels (default).  The CPU test injects oracle implementations with the same signatures.
+
+    `int8_k`: the rank quantises its OWN key rows and the exchange carries INT8 K (+ per-block scales and pooled means) instead
+    of 16-bit K; the key mean stays global and bit-identical to the single-GPU one because the ranks all-gather the 128-row
+    partial sums the single-GPU reduction is built from (tdb200_sla_kmean_partial / _final).  Served by the 128-wide softmax
+    kernel; other head dims / feature maps keep the 16-bit exchange."""
 
     def __init__(self, sla_module):
         self.sla = sla_module
+        self.int8_k = (getattr(sla_module, "quantised_qk", True) and getattr(sla_module, "feature", 0) == 0
+                       and os.environ.get("TDB200_SP_INT8_K", "1") != "0")       # "0": the 16-bit K exchange, for A/B timing
 
     def prepare_q(self, q):
         from .SLA.utils import quant_q_only
@@ -68,13 +78,41 @@ class GpuPrimitives:
         from .SLA.core import linear_moments
         return linear_moments(k_local, v_local)
 
+    # ---- INT8-K exchange ------------------------------------------------------------------------------------------------
+    def k_partials(self, k_local):
+        from .SLA.utils import kmean_partials
+        return kmean_partials(k_local)
+
+    def k_mean(self, partials, l_total):
+        from .SLA.utils import kmean_from_partials
+        return kmean_from_partials(partials, l_total)
+
+    def k_quant(self, k_local, kmean, k_i8_out=None):
+        from .SLA.utils import quant_k_seq
+        return quant_k_seq(k_local, kmean, k_i8_out)
+
+    def attention_i8(self, q, qprep, k_i8_full, k_scale, k_pool, kmean, v_full, lk, kv, ksum):
+        from .SLA.core import attn_fwd
+        from .SLA.utils import block_map_from_pools, cdiv as _cdiv, quant_q_only
+        sla = self.sla
+        d = q.shape[-1]
+        prep = qprep if qprep is not None else quant_q_only(q)
+        prep.kmean, prep.k_i8, prep.k_scale, prep.k_pool = kmean, k_i8_full, k_scale, k_pool
+        prep.nblk, prep.k_seq_major = _cdiv(lk, 64), True
+        topk = min(prep.nblk, int(sla.topk * prep.nblk))
+        _, lut = block_map_from_pools(prep.q_pool, prep.k_pool, topk)
+        kvw = torch.matmul(sla.proj_l.weight.float(), kv).to(q.dtype).contiguous()
+        return attn_fwd(prep, v_full, q, lut, topk, kvw, ksum, sla.proj_l.bias.float().contiguous(), d ** -0.5, lk=lk)
+
 
 class SPAttention:
     """Drop-in for the block's attention callable: (q, k, v) local [1, rows, H, D] -> [1, rows, H, D].
 
-    The block calls start_kv(k, v) as soon as K and V exist: both all-gathers and the moment all-reduces are issued
-    asynchronously (NCCL stream) and overlap with the Q projection, Q RMSNorm+RoPE and the Q-side quantisation that the
-    block and __call__ run before waiting on them."""
+    The block calls start_k(k) / start_kv(k, v) as soon as K and V exist: the exchanges are issued asynchronously (NCCL
+    stream) and overlap with the V and Q projections, Q RMSNorm+RoPE and the Q-side quantisation that the block and __call__
+    run before waiting on them.  With `prims.int8_k` the K exchange is: all-gather of the key-mean partials (tiny) -> global
+    mean -> local smoothing / INT8 / pooling -> all-gather of INT8 K [rows, H, D], k_scale and k_pool; otherwise the 16-bit K
+    slab is gathered and every rank prepares the whole key sequence."""
 
     def __init__(self, sp: "SequenceParallel", prims):
         self.sp, self.prims = sp, prims
@@ -82,53 +120,90 @@ class SPAttention:
         self._pending = None
         self._pending_k = None
 
-    def _gather_async(self, name: str, t: torch.Tensor):
-        """t [1, rows, H, D] -> ([1, world*rows_pad, H, D] buffer, NCCL work handle); zero-padded tail of the last rank."""
-        sp = self.sp
-        _, rows, h, d = t.shape
-        key = (name, h, d, t.dtype, t.device)
+    def _buf(self, name, shape, dtype, device, zero=False):
+        key = (name, tuple(shape), dtype, device)
         if key not in self._bufs:
-            self._bufs[key] = (torch.zeros(sp.rows_pad, h, d, dtype=t.dtype, device=t.device),
-                               torch.zeros(sp.world * sp.rows_pad, h, d, dtype=t.dtype, device=t.device))
-        send, recv = self._bufs[key]
-        send[:rows].copy_(t[0])
+            self._bufs[key] = (torch.zeros if zero else torch.empty)(*shape, dtype=dtype, device=device)
+        return self._bufs[key]
+
+    def _gather_async(self, name: str, t: torch.Tensor, pad_rows: int, copy: bool = True):
+        """t [rows, ...] -> ([world*pad_rows, ...] buffer, NCCL work handle); rows beyond t's stay zero (last rank).  With
+        copy=False `t` already IS the first rows of the send buffer (see send_buffer)."""
+        sp = self.sp
+        send = self.send_buffer(name, t.shape[1:], pad_rows, t.dtype, t.device)
+        if copy:
+            send[: t.shape[0]].copy_(t)
+        recv = self._buf(name + ".r", (sp.world * pad_rows, *t.shape[1:]), t.dtype, t.device)
         work = dist.all_gather_into_tensor(recv, send, group=sp.group, async_op=True)
-        return recv.unsqueeze(0), work
+        return recv, work
+
+    def send_buffer(self, name, tail_shape, pad_rows, dtype, device):
+        return self._buf(name + ".s", (pad_rows, *tail_shape), dtype, device, zero=True)
 
     def _cdt(self, t):
         return self.prims.sla.dtype if hasattr(self.prims, "sla") else t.dtype
 
+    def _use_int8(self, k):
+        return getattr(self.prims, "int8_k", False) and k.shape[-1] == 128
+
     def start_k(self, k):
-        """K exists (projected, normalised, rotated): start its all-gather; the V and Q projections run under it."""
+        """K exists (projected, normalised, rotated): start its exchange; the V and Q projections run under it."""
+        sp = self.sp
         k = k.to(self._cdt(k)).contiguous()
-        k_full, wk = self._gather_async("k", k)
-        self._pending_k = (k, k_full, wk)
+        if not self._use_int8(k):
+            k_full, wk = self._gather_async("k", k[0], sp.rows_pad)
+            self._pending_k = (k, ("bf16", k_full.unsqueeze(0)), [wk])
+            return
+        _, rows, h, d = k.shape
+        w, cp, nbp = sp.world, sp.rows_pad // 128, sp.rows_pad // 64
+        part = self.prims.k_partials(k)                                        # [1, H, ceil(rows/128), D]
+        recv, wp = self._gather_async("kpart", part[0].transpose(0, 1), cp)     # rows = chunks: [w*cp, H, D]
+        wp.wait()
+        chunks = cdiv(sp.total_rows, 128)
+        partials = recv[:chunks].transpose(0, 1).contiguous().unsqueeze(0)      # [1, H, chunks, D], global chunk order
+        kmean = self.prims.k_mean(partials, sp.total_rows)
+        send_k = self.send_buffer("k8", (h, d), sp.rows_pad, torch.int8, k.device)
+        k_i8, k_scale, k_pool = self.prims.k_quant(k, kmean, send_k[:rows].unsqueeze(0))
+        if k_i8.data_ptr() != send_k.data_ptr():                               # primitives that allocate their own output
+            send_k[:rows].copy_(k_i8[0])
+        k8_full, w1 = self._gather_async("k8", send_k[:rows], sp.rows_pad, copy=False)
+        ks_full, w2 = self._gather_async("kscale", k_scale[0].transpose(0, 1), nbp)          # [w*nbp, H]
+        kp_full, w3 = self._gather_async("kpool", k_pool[0].transpose(0, 1), nbp)            # [w*nbp, H, D]
+        self._pending_k = (k, ("int8", k8_full.unsqueeze(0), ks_full, kp_full, kmean), [w1, w2, w3])
 
     def start_kv(self, k, v):
         sp = self.sp
         cdt = self._cdt(k)
         if self._pending_k is None:
             self.start_k(k)
-        k, k_full, wk = self._pending_k
+        k, kx, works = self._pending_k
         self._pending_k = None
         v = v.to(cdt).contiguous()
-        v_full, wv = self._gather_async("v", v)
+        v_full, wv = self._gather_async("v", v[0], sp.rows_pad)
         kv, ksum = self.prims.moments(k, v)
         w1 = dist.all_reduce(kv, group=sp.group, async_op=True)
         w2 = dist.all_reduce(ksum, group=sp.group, async_op=True)
-        self._pending = (k_full, v_full, kv, ksum, (wk, wv, w1, w2))
+        self._pending = (kx, v_full.unsqueeze(0), kv, ksum, works + [wv, w1, w2])
 
     def __call__(self, q, k, v):
+        sp = self.sp
         dtype = q.dtype
         q = q.to(self._cdt(q)).contiguous()
         if self._pending is None:
             self.start_kv(k, v)
-        k_full, v_full, kv, ksum, works = self._pending
+        kx, v_full, kv, ksum, works = self._pending
         self._pending = None
         qprep = self.prims.prepare_q(q) if hasattr(self.prims, "prepare_q") else None  # overlaps with the collectives
         for w in works:
             w.wait()
-        out = self.prims.attention(q, k_full, v_full, self.sp.total_rows, kv, ksum, qprep)
+        if kx[0] == "bf16":
+            out = self.prims.attention(q, kx[1], v_full, sp.total_rows, kv, ksum, qprep)
+        else:
+            _, k8_full, ks_full, kp_full, kmean = kx
+            nblk = cdiv(sp.total_rows, 64)
+            k_scale = ks_full[:nblk].transpose(0, 1).contiguous().unsqueeze(0)             # [1, H, nblk]
+            k_pool = kp_full[:nblk].transpose(0, 1).contiguous().unsqueeze(0)              # [1, H, nblk, D]
+            out = self.prims.attention_i8(q, qprep, k8_full, k_scale, k_pool, kmean, v_full, sp.total_rows, kv, ksum)
         return out.to(dtype)
 
 
