@@ -80,6 +80,12 @@ int tdb200_gemm_w8a8(const int8_t* a_q, const float* a_s, const int8_t* b_q, con
 #define TDB200_EPILOGUE_GELU_TANH 1
 int tdb200_gemm_w8a8_ex(const int8_t* a_q, const float* a_s, const int8_t* b_q, const float* b_s, const void* bias,
                         void* c, int c_dtype, int64_t m, int64_t n, int64_t k, int epilogue, void* stream);
+/* One W8A8 GEMM for projections that share their input (the q/k/v of a self-attention; reference: the fused to_qkv / to_kv
+ * packing of TurboT2AV ltx_distillation/acceleration.py:836-860): b_q [n,k], b_s and bias are the row-wise concatenation of
+ * `parts` equal projections (n = parts * n_part, n_part a multiple of 256); c receives `parts` separate contiguous
+ * [m, n_part] matrices.  Scales are per 128 weight rows, so every output equals tdb200_gemm_w8a8 on its own weights. */
+int tdb200_gemm_w8a8_split(const int8_t* a_q, const float* a_s, const int8_t* b_q, const float* b_s, const void* bias,
+                           void* c, int c_dtype, int64_t m, int64_t n, int64_t k, int64_t parts, void* stream);
 /* GEMM whose output is emitted already block-quantised for the next W8A8 GEMM:
  *   (out_q, out_s) == tdb200_quant_int8_block128( output of tdb200_gemm_w8a8_ex in dtype `mid_dtype` )   bit for bit,
  * without the 16-bit tensor ever reaching HBM (FFN: Linear -> GELU -> Int8Linear, ops/core.py:28-57 called twice).

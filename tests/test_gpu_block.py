@@ -26,6 +26,27 @@ def test_block_matches_oracle(cuda, dim, heads, ffn, thw, lc, topk):
     assert out.dtype == x.dtype and out.shape == x.shape
 
 
+def test_fused_qkv_block_equals_the_unfused_one(cuda, monkeypatch):
+    """f2: the q/k/v projections as one split-output GEMM (block.FUSE_QKV) change nothing in the block's output (the
+    projections themselves are compared bit for bit in test_split_output_gemm_equals_the_separate_gemms; the block's output
+    can differ run to run in rare last-place roundings because the linear-attention moments are summed with fp32 atomics)."""
+    from turbodiffusion_b200 import block as B
+    dim, heads, ffn, thw = 512, 4, 1024, (3, 10, 23)
+    l = thw[0] * thw[1] * thw[2]
+    sd = B.random_block_state(dim, ffn, heads, seed=9, device=cuda)
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(l, dim, generator=g).bfloat16().to(cuda)
+    e0 = (torch.randn(6, dim, generator=g) * 0.1).to(cuda)
+    ctx = torch.randn(40, dim, generator=g).bfloat16().to(cuda)
+    ang = O.wan_rope_angles(*thw, dim // heads).to(cuda)
+    outs = {}
+    for mode in ("0", "1"):
+        monkeypatch.setattr(B, "FUSE_QKV", mode)
+        outs[mode] = B.WanBlockB200(sd, dim, heads, topk=0.3)(x, e0, ang, ctx)
+    diff = (outs["0"].float() - outs["1"].float())
+    assert (diff != 0).float().mean().item() < 1e-3 and (diff.norm() / outs["0"].float().norm()).item() < 1e-4
+
+
 def test_block_keeps_reference_state_dict_keys(cuda):
     from turbodiffusion_b200.block import LINEARS, random_block_state
     sd = random_block_state(256, 512, 2, seed=0, device=cuda)

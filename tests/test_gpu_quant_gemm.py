@@ -204,3 +204,29 @@ def test_gelu_epilogue_vs_oracle_gelu(cuda, m, n, k):
     dq3 = (q3.cpu().to(torch.int16) - q_ref.to(torch.int16)).abs()
     assert dq3.max().item() <= 1 and (dq3 > 0).float().mean().item() < 2e-2, (dq3.max().item(), (dq3 > 0).float().mean().item())
     assert ((s3.cpu() - s_ref).abs() <= 2.0 ** -7 * s_ref).all()
+
+
+@pytest.mark.parametrize("m,n_part,k,parts,dtype", [(1000, 256, 384, 3, torch.bfloat16), (130, 512, 128, 2, torch.float16),
+                                                   (32760, 1536, 1536, 3, torch.bfloat16)])
+def test_split_output_gemm_equals_the_separate_gemms(cuda, m, n_part, k, parts, dtype):
+    """f2: one GEMM against row-concatenated projection weights, outputs as `parts` contiguous matrices (the fused q/k/v of
+    block.py; packing of acceleration.py:836-860) == the projections' own GEMMs bit for bit, including the ragged last row
+    tile of every part (the 3-D store map clips rows past m per part)."""
+    from turbodiffusion_b200 import ops
+    from turbodiffusion_b200.turbo_diffusion_ops import gemm_cuda_split, gemm_cuda_swizzle_bias
+    g = torch.Generator().manual_seed(m + parts)
+    x = torch.randn(m, k, generator=g).to(dtype).to(cuda)
+    xq, xs = ops.int8_quant(x)
+    ws = [ops.int8_quant((torch.randn(n_part, k, generator=g) * k ** -0.5).to(dtype).to(cuda)) for _ in range(parts)]
+    bs = [(torch.randn(n_part, generator=g) * 0.1).to(dtype).to(cuda) for _ in range(parts)]
+    guard = torch.full((parts + 1, m, n_part), 7.0, dtype=dtype, device=cuda)       # detects writes past the last part
+    fused = gemm_cuda_split(xq, xs, torch.cat([w[0] for w in ws]), torch.cat([w[1] for w in ws]), torch.cat(bs), dtype, parts)
+    assert fused.shape == (parts, m, n_part) and fused.is_contiguous()
+    for i in range(parts):
+        y = torch.empty(m, n_part, dtype=dtype, device=cuda)
+        gemm_cuda_swizzle_bias(xq, xs, ws[i][0], ws[i][1], y, bs[i])
+        assert torch.equal(fused[i], y), i
+    assert (guard == 7.0).all()
+    with pytest.raises(RuntimeError):
+        gemm_cuda_split(xq, xs, torch.cat([w[0] for w in ws])[: parts * n_part - 128], torch.cat([w[1] for w in ws])[:-1],
+                        None, dtype, parts)       # parts must be equal multiples of 256 columns

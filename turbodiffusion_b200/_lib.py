@@ -25,6 +25,7 @@ _PROTOS = {
     "tdb200_gelu_quant_int8_block128": [_P, _I, _I64, _I64, _P, _P, _P],
     "tdb200_gemm_w8a8": [_P, _P, _P, _P, _P, _P, _I, _I64, _I64, _I64, _P],
     "tdb200_gemm_w8a8_ex": [_P, _P, _P, _P, _P, _P, _I, _I64, _I64, _I64, _I, _P],
+    "tdb200_gemm_w8a8_split": [_P, _P, _P, _P, _P, _P, _I, _I64, _I64, _I64, _I64, _P],
     "tdb200_gemm_w8a8_quant_out": [_P, _P, _P, _P, _P, _P, _P, _I, _I64, _I64, _I64, _I, _P],
     "tdb200_rms_norm_f32": [_P, _P, _P, _I64, _I64, _F, _P],
     "tdb200_layer_norm_f32": [_P, _P, _P, _P, _I64, _I64, _F, _P],

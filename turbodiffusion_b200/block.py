@@ -20,8 +20,8 @@ import torch.nn.functional as F
 
 from . import ops
 from .SLA.core import SageSparseLinearAttention, SparseLinearAttention
-from .turbo_diffusion_ops import (gelu_quant_cuda, gemm_cuda_bias_gelu, gemm_cuda_quant_out, gemm_cuda_swizzle_bias,
-                                  quant_cuda)
+from .turbo_diffusion_ops import (gelu_quant_cuda, gemm_cuda_bias_gelu, gemm_cuda_quant_out, gemm_cuda_split,
+                                  gemm_cuda_swizzle_bias, quant_cuda)
 
 # FFN activation between the two W8A8 GEMMs:
 #   "fused": bias + GELU (one-MUFU tanh) + quantisation in the up-projection's epilogue: no 16-bit intermediate in HBM; the
@@ -31,6 +31,13 @@ from .turbo_diffusion_ops import (gelu_quant_cuda, gemm_cuda_bias_gelu, gemm_cud
 # Measured in the step (profiles/r02_bench_ffn_modes.txt), both with packed arithmetic: fused 99.7 ms (up-projection 0.660 ms at shape A),
 # split 102.0 ms (0.492 ms + 0.200 ms) per denoise step -> fused is the default.
 FFN_ACT_MODE = os.environ.get("TDB200_FFN_ACT", "fused")
+
+# Self-attention q/k/v as ONE GEMM against the row-concatenated weights (the packing of the LTX client's fused to_qkv,
+# acceleration.py:836-860), outputs written as three contiguous matrices: bit-identical to the three GEMMs (scales are per
+# 128 weight rows), 31.1 -> 32 tile waves instead of 3 x (10.4 -> 11) at shape A and two launches fewer.
+#   "1": always, "0": never, "auto": single GPU yes; under a sequence-parallel hook no (the separate K projection lets the
+#   K exchange start under the V and Q projections)
+FUSE_QKV = os.environ.get("TDB200_FUSE_QKV", "auto")
 
 LINEARS = ("self_attn.q", "self_attn.k", "self_attn.v", "self_attn.o", "cross_attn.q", "cross_attn.k", "cross_attn.v",
            "cross_attn.o", "ffn.0", "ffn.2")
@@ -83,6 +90,17 @@ class WanBlockB200:
             self.sla.proj_l.weight.copy_(sd["self_attn.attn_op.local_attn.proj_l.weight"])
             self.sla.proj_l.bias.copy_(sd["self_attn.attn_op.local_attn.proj_l.bias"])
         self.attn_hook = None  # sequence-parallel wrapper installs its own attention callable here
+        self._qkv = None       # (int8_weight [3*dim, dim], scale, bias) built on first use
+
+    def _fused_qkv(self):
+        if self._qkv is None:
+            sd = self.sd
+            names = ("self_attn.q", "self_attn.k", "self_attn.v")
+            if sd[names[0] + ".int8_weight"].shape[0] % 256:
+                raise ValueError("fused q/k/v needs dim % 256 == 0")
+            self._qkv = tuple(torch.cat([sd[n + suffix] for n in names], dim=0).contiguous()
+                              for suffix in (".int8_weight", ".scale", ".bias"))
+        return self._qkv
 
     # -- helpers -----------------------------------------------------------------------------------------------
     def _gemm(self, xq, xs, name, dtype, gelu=False):
@@ -114,21 +132,25 @@ class WanBlockB200:
         # K and V first: the all-gather hook starts their exchange while Q is still being produced.  The head<->sequence
         # hook asks for Q first instead (its last exchange is hidden by the K/Q-side preparation, see dist.py).
         attn = self.attn_hook or self.sla
+        fuse = FUSE_QKV == "1" or (FUSE_QKV == "auto" and self.attn_hook is None and dim % 256 == 0)
+        if fuse:
+            wq, ws, wb = self._fused_qkv()
+            q_raw, k_raw, v = gemm_cuda_split(xq, xs, wq, ws, wb, x.dtype, 3).unbind(0)
+            proj = {"q": lambda: q_raw, "k": lambda: k_raw, "v": lambda: v}
+        else:
+            proj = {n: (lambda n=n: self._gemm(xq, xs, "self_attn." + n, x.dtype)) for n in ("q", "k", "v")}
         q = None
         if getattr(attn, "q_first", False):
-            q = self._gemm(xq, xs, "self_attn.q", x.dtype)
-            q = ops.rmsnorm_rope(q, sd["self_attn.norm_q.weight"], angles, eps, h)
+            q = ops.rmsnorm_rope(proj["q"](), sd["self_attn.norm_q.weight"], angles, eps, h)
             attn.start_q(q.view(1, l, h, d))
-        k = self._gemm(xq, xs, "self_attn.k", x.dtype)
-        k = ops.rmsnorm_rope(k, sd["self_attn.norm_k.weight"], angles, eps, h)
+        k = ops.rmsnorm_rope(proj["k"](), sd["self_attn.norm_k.weight"], angles, eps, h)
         if hasattr(attn, "start_k"):
             attn.start_k(k.view(1, l, h, d))
-        v = self._gemm(xq, xs, "self_attn.v", x.dtype)
+        v = proj["v"]()
         if hasattr(attn, "start_kv"):
             attn.start_kv(k.view(1, l, h, d), v.view(1, l, h, d))
         if q is None:
-            q = self._gemm(xq, xs, "self_attn.q", x.dtype)
-            q = ops.rmsnorm_rope(q, sd["self_attn.norm_q.weight"], angles, eps, h)
+            q = ops.rmsnorm_rope(proj["q"](), sd["self_attn.norm_q.weight"], angles, eps, h)
         a = attn(q.view(1, l, h, d), k.view(1, l, h, d), v.view(1, l, h, d)).reshape(l, dim)
         y = self._linear(a, "self_attn.o")
         x = ops.gate_residual(x, y, e[2])  # x + y * e[2] (:405-406)

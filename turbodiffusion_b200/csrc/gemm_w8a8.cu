@@ -64,7 +64,14 @@ struct GemmParams {
   int act;  // 0 none, 1 GELU(tanh) applied to the T-rounded (acc [+ bias]) value, result rounded to T again
   int8_t* out_q;  // when non-NULL: emit quant_int8_block128(T output) instead of the T output itself
   float* out_s;   // [ceil(m/128), n/128]
+  int n_part;     // 16-bit output: columns per output matrix; c is [n / n_part, m, n_part] (n_part == n: the plain [m, n])
 };
+
+// 16-bit output box -> c [n / n_part, m, n_part]: the map is (column in part, row, part), so rows past m are clipped per part
+__device__ __forceinline__ void store_c(const void* tmap, const void* stage, int32_t col, int32_t row, int32_t n_part) {
+  const int32_t part = col / n_part;
+  tma_store_4d(tmap, stage, col - part * n_part, row, part, 0);
+}
 
 // kCluster: CTAs are launched as clusters of 2 that work on vertically adjacent tiles (m, n) and (m+1, n).  Each CTA
 // loads its own A tile and HALF of the shared B tile, multicasting that half to both CTAs: 32 KB instead of 48 KB cross
@@ -445,7 +452,7 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           __syncwarp();
           if (lane == 0) {
             if (half_active) {
-              tma_store_2d(&tmap_c, stage, int32_t(col0), int32_t(row0));
+              store_c(&tmap_c, stage, int32_t(col0), int32_t(row0), p.n_part);
               tma_store_commit();
             }
             tma_store_wait_read<0>();
@@ -473,10 +480,10 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       __syncwarp();
       if (lane == 0 && half_active) {
         if (kStoreRounds == 1) {
-          tma_store_2d(&tmap_c, stage, int32_t(col0), int32_t(row0));
-          if (col0 + 64 < p.n) tma_store_2d(&tmap_c, stage + 4096, int32_t(col0 + 64), int32_t(row0));
+          store_c(&tmap_c, stage, int32_t(col0), int32_t(row0), p.n_part);
+          if (col0 + 64 < p.n) store_c(&tmap_c, stage + 4096, int32_t(col0 + 64), int32_t(row0), p.n_part);
         } else if (col0 + 64 < p.n) {
-          tma_store_2d(&tmap_c, stage, int32_t(col0 + 64), int32_t(row0));
+          store_c(&tmap_c, stage, int32_t(col0 + 64), int32_t(row0), p.n_part);
         }
         tma_store_commit();
       }
@@ -532,7 +539,7 @@ extern "C" int tdb200_gemm_w8a8(const int8_t* a_q, const float* a_s, const int8_
 
 static int gemm_impl(const int8_t* a_q, const float* a_s, const int8_t* b_q, const float* b_s, const void* bias, void* c,
                      int8_t* out_q, float* out_s, int c_dtype, int64_t m, int64_t n, int64_t k, int epilogue, void* stream,
-                     bool row_scale = false);
+                     bool row_scale = false, int64_t parts = 1);
 
 extern "C" int tdb200_gemm_w8a8_ex(const int8_t* a_q, const float* a_s, const int8_t* b_q, const float* b_s,
                                    const void* bias, void* c, int c_dtype, int64_t m, int64_t n, int64_t k,
@@ -556,10 +563,23 @@ extern "C" int tdb200_gemm_w8a8_rowwise(const int8_t* a_q, const float* a_s, con
   return gemm_impl(a_q, a_s, b_q, b_s, bias, c, nullptr, nullptr, c_dtype, m, n, k, TDB200_EPILOGUE_NONE, stream, true);
 }
 
+// one GEMM for several projections that share their input (q/k/v): b_q / b_s / bias are the row-wise concatenation of the
+// projections' weights (n = parts * n_part, n_part a multiple of 256), the outputs are written as `parts` separate contiguous
+// [m, n_part] matrices c[0..parts).  Block scales are per 128 weight rows, so each output equals its own GEMM bit for bit.
+extern "C" int tdb200_gemm_w8a8_split(const int8_t* a_q, const float* a_s, const int8_t* b_q, const float* b_s,
+                                      const void* bias, void* c, int c_dtype, int64_t m, int64_t n, int64_t k,
+                                      int64_t parts, void* stream) {
+  if (!c) return tdb::fail(TDB200_ERR_INVALID_ARG, "gemm_w8a8_split: null pointer");
+  return gemm_impl(a_q, a_s, b_q, b_s, bias, c, nullptr, nullptr, c_dtype, m, n, k, TDB200_EPILOGUE_NONE, stream, false, parts);
+}
+
 static int gemm_impl(const int8_t* a_q, const float* a_s, const int8_t* b_q, const float* b_s, const void* bias, void* c,
                      int8_t* out_q, float* out_s, int c_dtype, int64_t m, int64_t n, int64_t k, int epilogue, void* stream,
-                     bool row_scale) {
+                     bool row_scale, int64_t parts) {
   using namespace tdb;
+  if (parts < 1 || n % parts != 0 || (parts > 1 && (n / parts) % BN != 0))
+    return fail(TDB200_ERR_UNSUPPORTED, "gemm_w8a8_split: n=%lld must split into %lld parts of a multiple of %d columns",
+                (long long)n, (long long)parts, BN);
   if (epilogue != TDB200_EPILOGUE_NONE && epilogue != TDB200_EPILOGUE_GELU_TANH)
     return fail(TDB200_ERR_INVALID_ARG, "gemm_w8a8_ex: unknown epilogue %d", epilogue);
   if (!a_q || !a_s || !b_q || !b_s || !c) return fail(TDB200_ERR_INVALID_ARG, "gemm_w8a8: null pointer");
@@ -591,7 +611,11 @@ static int gemm_impl(const int8_t* a_q, const float* a_s, const int8_t* b_q, con
       return rc;
   } else {
     const CUtensorMapDataType t16 = c_dtype == TDB200_DTYPE_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
-    if (int rc = make_tmap_2d(&tc, c, t16, 2, uint64_t(n), uint64_t(m), uint64_t(n) * 2, 64, 32)) return rc;
+    const uint64_t n_part = uint64_t(n / parts);
+    const uint64_t dims[4] = {n_part, uint64_t(m), uint64_t(parts), 1};
+    const uint64_t str[3] = {n_part * 2, uint64_t(m) * n_part * 2, uint64_t(m) * uint64_t(n) * 2};
+    const uint32_t box[4] = {64, 32, 1, 1};
+    if (int rc = make_tmap_4d(&tc, c, t16, 2, dims, str, box)) return rc;
   }
 
   GemmParams p;
@@ -605,6 +629,7 @@ static int gemm_impl(const int8_t* a_q, const float* a_s, const int8_t* b_q, con
   p.act = epilogue;
   p.out_q = out_q;
   p.out_s = out_s;
+  p.n_part = static_cast<int>(n / parts);
   p.k_blocks = static_cast<int>(k / BK);
   p.n_tiles = static_cast<int>(cdiv64(n, BN));
   p.m_tiles = static_cast<int>(m_tiles);

@@ -111,3 +111,41 @@ class PostScaleInt8Linear(torch.nn.Module):
         if lin.bias is not None:
             layer.bias.copy_(lin.bias.detach().to(torch.bfloat16))
         return layer
+
+    @classmethod
+    def from_tilelang_linears(cls, linears):
+        """tilelang_w8a8.py:229-258: one layer for projections that share their input (to_q/to_k/to_v -> to_qkv, to_k/to_v ->
+        to_kv): INT8 weights, per-output-channel scales and biases concatenated along the output dimension.  The scales are
+        per channel, so `fused(x).split(...)` equals the separate layers' outputs bit for bit."""
+        if not linears:
+            raise ValueError("Expected at least one PostScaleInt8Linear")
+        k = linears[0].in_features
+        if any(lin.in_features != k for lin in linears):
+            raise ValueError("Fused W8A8 linears must share in_features")
+        dev = linears[0].int8_weight.device
+        if any(lin.int8_weight.device != dev for lin in linears):
+            raise ValueError("Fused W8A8 linears must share a device")
+        fused = cls(k, sum(lin.out_features for lin in linears), bias=any(lin._had_bias for lin in linears),
+                    dtype=linears[0].bias.dtype).to(dev)
+        fused.int8_weight.copy_(torch.cat([lin.int8_weight for lin in linears], dim=0))
+        fused.scale.copy_(torch.cat([lin.scale for lin in linears], dim=0))
+        fused.bias.copy_(torch.cat([lin.bias if lin._had_bias else torch.zeros_like(lin.bias) for lin in linears], dim=0))
+        return fused
+
+
+def fuse_attention_projections(model: torch.nn.Module) -> int:
+    """fuse_tilelang_attention_projections (acceleration.py:836-860): every module whose to_q/to_k/to_v are PostScaleInt8Linear
+    with equal in_features gains `to_qkv`; equal to_k/to_v in_features gains `to_kv` (what ltx_core's Attention.forward looks
+    up, attention.py:186-193).  Returns the number of fused layers added."""
+    fused = 0
+    for module in model.modules():
+        if not all(isinstance(getattr(module, a, None), PostScaleInt8Linear) for a in ("to_k", "to_v")):
+            continue
+        if isinstance(getattr(module, "to_q", None), PostScaleInt8Linear) and (
+                module.to_q.in_features == module.to_k.in_features == module.to_v.in_features):
+            module.to_qkv = PostScaleInt8Linear.from_tilelang_linears((module.to_q, module.to_k, module.to_v))
+            fused += 1
+        if module.to_k.in_features == module.to_v.in_features:
+            module.to_kv = PostScaleInt8Linear.from_tilelang_linears((module.to_k, module.to_v))
+            fused += 1
+    return fused

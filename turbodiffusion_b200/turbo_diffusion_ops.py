@@ -98,6 +98,20 @@ def gemm_cuda_bias_gelu(a_q, a_s, b_q, b_s, c, bias) -> None:
     _gemm(a_q, a_s, b_q, b_s, c, bias, epilogue=1)
 
 
+def gemm_cuda_split(a_q, a_s, b_q, b_s, bias, out_dtype, parts: int):
+    """One GEMM against `parts` row-concatenated projection weights (b_q [parts*n, k], b_s, bias); returns the outputs as a
+    [parts, m, n] tensor of separate contiguous matrices (each bit-identical to its own gemm_cuda_swizzle_bias call)."""
+    require_cuda(a_q, a_s, b_q, b_s, bias)
+    m, n, k = a_q.size(0), b_q.size(0), b_q.size(1)
+    c = torch.empty((parts, m, n // parts), dtype=out_dtype, device=a_q.device)
+    if bias is not None and bias.dtype != out_dtype:
+        bias = bias.to(out_dtype)
+    with (GEMM_TIMER(m, n, k) if GEMM_TIMER is not None else contextlib.nullcontext()):
+        check(lib().tdb200_gemm_w8a8_split(ptr(a_q), ptr(a_s), ptr(b_q), ptr(b_s), ptr(bias), ptr(c), DTYPE_TAG[out_dtype],
+                                           m, n, k, parts, stream_ptr(a_q.device)), "gemm_cuda_split")
+    return c
+
+
 def gemm_cuda_quant_out(a_q, a_s, b_q, b_s, bias, mid_dtype, gelu: bool = False):
     """(q, s) = quant_cuda(act(gemm + bias)) in one kernel; the 16-bit activation never reaches HBM."""
     require_cuda(a_q, a_s, b_q, b_s, bias)
