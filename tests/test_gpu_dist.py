@@ -48,10 +48,6 @@ def _worker(rank, world, port, out_path, mode, dim, heads):
 def test_sequence_parallel_matches_single_gpu(tmp_path, mode, dim, heads):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
-    if heads % 2 and not os.environ.get("TDB200_TEST_UNEVEN_HEADS"):
-        # written after round 1's GPU budget was spent: validated with gloo on CPU (tests/test_dist_cpu.py), first GPU run
-        # is tools/gpu_scaling.sh (which sets the variable); until then it must not stop a `pytest -x` run
-        pytest.skip("uneven-head split: set TDB200_TEST_UNEVEN_HEADS=1 (first GPU run pending)")
     import torch.multiprocessing as mp
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
@@ -60,5 +56,7 @@ def test_sequence_parallel_matches_single_gpu(tmp_path, mode, dim, heads):
     out = str(tmp_path / "sp.pt")
     mp.spawn(_worker, args=(2, port, out, mode, dim, heads), nprocs=2, join=True)
     res = torch.load(out)
-    # identical arithmetic per row; only the fp32 atomics order of the linear-attention moments differs (both modes)
-    assert res["rel_l2"] < 2e-3, res
+    # identical arithmetic per row; only the fp32 summation order of the linear-attention moments differs (atomics, and the
+    # all-reduce in the all-gather mode), which moves the 16-bit kvw operand and through it many outputs by one unit in the
+    # last place: measured 1e-3 .. 2.4e-3 (uneven-head split) with max |diff| = 1 bf16 ulp of the largest outputs
+    assert res["rel_l2"] < 4e-3 and res["max_abs"] <= 0.0625, res
