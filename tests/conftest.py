@@ -18,3 +18,11 @@ def cuda():
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     return torch.device("cuda:0")
+
+
+@pytest.fixture(autouse=True)
+def _seed_global_rng():
+    """Tests that draw from torch's global generator see the same data whatever ran before them (test order, -k selections)."""
+    import torch
+    torch.manual_seed(20240917)
+    yield

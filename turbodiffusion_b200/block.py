@@ -36,7 +36,8 @@ FFN_ACT_MODE = os.environ.get("TDB200_FFN_ACT", "fused")
 # acceleration.py:836-860), outputs written as three contiguous matrices: bit-identical to the three GEMMs (scales are per
 # 128 weight rows), 31.1 -> 32 tile waves instead of 3 x (10.4 -> 11) at shape A and two launches fewer.
 #   "1": always, "0": never, "auto": single GPU yes; under a sequence-parallel hook no (the separate K projection lets the
-#   K exchange start under the V and Q projections)
+#   K exchange start under the V and Q projections).  Unless "0" the cross-attention k/v of the text tokens are one GEMM too
+#   (M = 512 rows: 24 tiles per projection on 148 SMs, so the fused launch costs what one of the two did).
 FUSE_QKV = os.environ.get("TDB200_FUSE_QKV", "auto")
 
 LINEARS = ("self_attn.q", "self_attn.k", "self_attn.v", "self_attn.o", "cross_attn.q", "cross_attn.k", "cross_attn.v",
@@ -90,17 +91,17 @@ class WanBlockB200:
             self.sla.proj_l.weight.copy_(sd["self_attn.attn_op.local_attn.proj_l.weight"])
             self.sla.proj_l.bias.copy_(sd["self_attn.attn_op.local_attn.proj_l.bias"])
         self.attn_hook = None  # sequence-parallel wrapper installs its own attention callable here
-        self._qkv = None       # (int8_weight [3*dim, dim], scale, bias) built on first use
+        self._packed = {}      # fused projection weights (int8_weight, scale, bias), built on first use
 
-    def _fused_qkv(self):
-        if self._qkv is None:
+    def _fused(self, *names):
+        """Row-concatenated weights of projections that share their input (self-attention q/k/v, cross-attention k/v)."""
+        if names not in self._packed:
             sd = self.sd
-            names = ("self_attn.q", "self_attn.k", "self_attn.v")
-            if sd[names[0] + ".int8_weight"].shape[0] % 256:
-                raise ValueError("fused q/k/v needs dim % 256 == 0")
-            self._qkv = tuple(torch.cat([sd[n + suffix] for n in names], dim=0).contiguous()
-                              for suffix in (".int8_weight", ".scale", ".bias"))
-        return self._qkv
+            if any(sd[n + ".int8_weight"].shape[0] % 256 for n in names):
+                raise ValueError("fused projections need out_features % 256 == 0")
+            self._packed[names] = tuple(torch.cat([sd[n + suffix] for n in names], dim=0).contiguous()
+                                        for suffix in (".int8_weight", ".scale", ".bias"))
+        return self._packed[names]
 
     # -- helpers -----------------------------------------------------------------------------------------------
     def _gemm(self, xq, xs, name, dtype, gelu=False):
@@ -134,7 +135,7 @@ class WanBlockB200:
         attn = self.attn_hook or self.sla
         fuse = FUSE_QKV == "1" or (FUSE_QKV == "auto" and self.attn_hook is None and dim % 256 == 0)
         if fuse:
-            wq, ws, wb = self._fused_qkv()
+            wq, ws, wb = self._fused("self_attn.q", "self_attn.k", "self_attn.v")
             q_raw, k_raw, v = gemm_cuda_split(xq, xs, wq, ws, wb, x.dtype, 3).unbind(0)
             proj = {"q": lambda: q_raw, "k": lambda: k_raw, "v": lambda: v}
         else:
@@ -158,8 +159,12 @@ class WanBlockB200:
         # ---- cross-attention over the text tokens (:410, 277-298); dense SDPA stays a library call (512 keys)
         hn = ops.fast_layernorm(x, sd["norm3.weight"], sd["norm3.bias"], eps)
         cq = ops.fast_rmsnorm(self._linear(hn, "cross_attn.q"), sd["cross_attn.norm_q.weight"], eps)
-        ck = ops.fast_rmsnorm(self._linear(context, "cross_attn.k"), sd["cross_attn.norm_k.weight"], eps)
-        cv = self._linear(context, "cross_attn.v")
+        cxq, cxs = quant_cuda(context)      # one quantisation of the text tokens for both projections
+        if FUSE_QKV != "0" and dim % 256 == 0:
+            ck, cv = gemm_cuda_split(cxq, cxs, *self._fused("cross_attn.k", "cross_attn.v"), x.dtype, 2).unbind(0)
+        else:
+            ck, cv = self._gemm(cxq, cxs, "cross_attn.k", x.dtype), self._gemm(cxq, cxs, "cross_attn.v", x.dtype)
+        ck = ops.fast_rmsnorm(ck, sd["cross_attn.norm_k.weight"], eps)
         lc = context.shape[0]
         ca = F.scaled_dot_product_attention(cq.view(1, l, h, d).transpose(1, 2), ck.view(1, lc, h, d).transpose(1, 2),
                                             cv.view(1, lc, h, d).transpose(1, 2))
