@@ -195,8 +195,9 @@ def test_split_heads():
 
 def test_pick_mode():
     sp = SequenceParallel(32760, world=8, rank=0)
-    assert sp.pick_mode(12) == "allgather" and sp.pick_mode(40) == "ulysses" and sp.pick_mode(40, "allgather") == "allgather"
-    assert sp.pick_mode(12, "ulysses") == "ulysses"          # uneven head split (opt-in)
+    assert sp.pick_mode(12) == "ulysses" and sp.pick_mode(40) == "ulysses" and sp.pick_mode(40, "allgather") == "allgather"
+    assert sp.pick_mode(4) == "allgather"                    # fewer heads than ranks: only the all-gather mode applies
+    assert sp.pick_mode(12, "ulysses") == "ulysses"          # uneven head split (measured faster at N=8)
     with pytest.raises(ValueError):
         sp.pick_mode(4, "ulysses")                             # fewer heads than ranks
     assert SequenceParallel(32760, world=1, rank=0).pick_mode(12) == "allgather"

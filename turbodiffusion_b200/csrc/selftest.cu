@@ -150,6 +150,9 @@ extern "C" int tdb200_selftest_tmem_read(int warps, int iters, int convert, long
 // XU (MUFU) throughput probe: every thread runs `iters` rounds of 8 independent chains of one transcendental.
 //   mode 0: ex2.approx.ftz.f32        1: ex2.approx.ftz.bf16x2      2: ex2.approx.f16x2
 //   mode 3: tanh.approx.f32           4: tanh.approx.bf16x2         5: tanh.approx.f16x2
+//   mode 6: cvt.rn.bf16x2.f32 (F2FP pack; + one shift to close the chain)      7: cvt.rn.f16x2.f32 (+ shift)
+//   mode 8: cvt.rni.s32.f32 + cvt.rn.f32.s32 (F2I + I2F)                        9: mul.f32 (FMA-pipe baseline)
+//   mode 10: ex2.approx.ftz.f32 on chains 0-3 and cvt.rn.bf16x2.f32 on chains 4-7 (do the two share a pipe?)
 // Reports cycles per CTA (one CTA per SM, `warps` warps); results per clk per SM = warps*32*8*iters*(1 or 2)/cycles.
 // Decides whether the packed 16-bit forms deliver two results per XU issue slot (softmax / GELU epilogue design input).
 // ---------------------------------------------------------------------------------------------------------------
@@ -160,7 +163,7 @@ __global__ void __launch_bounds__(1024, 1) mufu_probe_kernel(int iters, long lon
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const float f = -0.001f * float(threadIdx.x + 1) - 0.01f * float(j);
-    if (kMode == 0 || kMode == 3) {
+    if (kMode == 0 || kMode == 3 || kMode >= 6) {
       x[j] = __float_as_uint(f);
     } else if (kMode == 1 || kMode == 4) {
       __nv_bfloat162 v = __floats2bfloat162_rn(f, f * 0.5f);
@@ -181,6 +184,12 @@ __global__ void __launch_bounds__(1024, 1) mufu_probe_kernel(int iters, long lon
       if (kMode == 3) asm volatile("tanh.approx.f32 %0, %0;" : "+r"(x[j]));
       if (kMode == 4) asm volatile("tanh.approx.bf16x2 %0, %0;" : "+r"(x[j]));
       if (kMode == 5) asm volatile("tanh.approx.f16x2 %0, %0;" : "+r"(x[j]));
+      if (kMode == 6 || (kMode == 10 && j >= 4))
+        asm volatile("{ .reg .b32 t; cvt.rn.bf16x2.f32 t, %0, %0; shl.b32 %0, t, 16; }" : "+r"(x[j]));
+      if (kMode == 7) asm volatile("{ .reg .b32 t; cvt.rn.f16x2.f32 t, %0, %0; shl.b32 %0, t, 13; }" : "+r"(x[j]));
+      if (kMode == 8) asm volatile("{ .reg .s32 t; cvt.rni.s32.f32 t, %0; cvt.rn.f32.s32 %0, t; }" : "+r"(x[j]));
+      if (kMode == 9) asm volatile("mul.f32 %0, %0, 0f3F7FFFF0;" : "+r"(x[j]));
+      if (kMode == 10 && j < 4) asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+r"(x[j]));
     }
   }
   __syncthreads();
@@ -195,8 +204,8 @@ __global__ void __launch_bounds__(1024, 1) mufu_probe_kernel(int iters, long lon
 
 extern "C" int tdb200_selftest_mufu(int mode, int warps, int iters, long long* cycles_per_cta, float* sink, void* stream) {
   using namespace tdb;
-  if (!cycles_per_cta || !sink || warps < 1 || warps > 32 || mode < 0 || mode > 5)
-    return fail(TDB200_ERR_INVALID_ARG, "selftest_mufu: mode in [0,5], warps in [1,32]");
+  if (!cycles_per_cta || !sink || warps < 1 || warps > 32 || mode < 0 || mode > 10)
+    return fail(TDB200_ERR_INVALID_ARG, "selftest_mufu: mode in [0,10], warps in [1,32]");
   if (int rc = require_sm100()) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int grid = sm_count();
@@ -206,7 +215,12 @@ extern "C" int tdb200_selftest_mufu(int mode, int warps, int iters, long long* c
     case 2: mufu_probe_kernel<2><<<grid, warps * 32, 0, st>>>(iters, cycles_per_cta, sink); break;
     case 3: mufu_probe_kernel<3><<<grid, warps * 32, 0, st>>>(iters, cycles_per_cta, sink); break;
     case 4: mufu_probe_kernel<4><<<grid, warps * 32, 0, st>>>(iters, cycles_per_cta, sink); break;
-    default: mufu_probe_kernel<5><<<grid, warps * 32, 0, st>>>(iters, cycles_per_cta, sink); break;
+    case 5: mufu_probe_kernel<5><<<grid, warps * 32, 0, st>>>(iters, cycles_per_cta, sink); break;
+    case 6: mufu_probe_kernel<6><<<grid, warps * 32, 0, st>>>(iters, cycles_per_cta, sink); break;
+    case 7: mufu_probe_kernel<7><<<grid, warps * 32, 0, st>>>(iters, cycles_per_cta, sink); break;
+    case 8: mufu_probe_kernel<8><<<grid, warps * 32, 0, st>>>(iters, cycles_per_cta, sink); break;
+    case 9: mufu_probe_kernel<9><<<grid, warps * 32, 0, st>>>(iters, cycles_per_cta, sink); break;
+    default: mufu_probe_kernel<10><<<grid, warps * 32, 0, st>>>(iters, cycles_per_cta, sink); break;
   }
   return check_launch("mufu_probe_kernel");
 }

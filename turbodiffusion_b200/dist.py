@@ -316,7 +316,8 @@ def split_heads(heads: int, world: int):
 class UnevenUlyssesAttention(UlyssesAttention):
     """The same exchange when heads % world != 0 (e.g. the 12 heads of Wan-1.3B on 8 GPUs -> 2,2,2,2,1,1,1,1): rank r takes
     the contiguous head range split_heads() assigns it; every all-to-all uses per-peer split sizes in units of one
-    [D]-row (rows * heads_of_peer).  Opt-in (`mode="ulysses"`); validated on CPU (gloo), not yet timed on GPUs."""
+    [D]-row (rows * heads_of_peer).  The slab <-> per-peer-chunk reordering is ONE gather kernel each way (a precomputed row
+    permutation), not one copy per peer.  Measured on 8 B200s at shape A: 26.4 ms/step vs 30.4 for the all-gather mode."""
 
     def __init__(self, sp: "SequenceParallel", prims, heads: int, compute_dtype=None):
         super().__init__(sp, prims, compute_dtype)
@@ -324,20 +325,27 @@ class UnevenUlyssesAttention(UlyssesAttention):
             raise ValueError(f"Ulysses exchange needs at least one head per rank (heads={heads}, world={sp.world})")
         self.heads = heads
         self.heads_of, self.head_off = split_heads(heads, sp.world)
+        self._perm = {}
+
+    def _perms(self, device):
+        """send position p (chunk j = rank j's heads of my rows, laid out [rows, heads_of[j]]) <-> slab row r*H + head."""
+        if device not in self._perm:
+            rows, h = self.sp.local_rows, self.heads
+            r = torch.arange(rows).view(rows, 1)
+            perm = torch.cat([(r * h + torch.arange(self.head_off[j], self.head_off[j] + self.heads_of[j]).view(1, -1)).reshape(-1)
+                              for j in range(self.sp.world)])
+            self._perm[device] = (perm.to(device), torch.argsort(perm).to(device))
+        return self._perm[device]
 
     def _to_heads_async(self, name: str, t: torch.Tensor):
         """t [1, rows, H, D] -> ([L, heads_of[rank], D] buffer, work handle)."""
-        sp, w = self.sp, self.sp.world
+        sp = self.sp
         t = (t if self.cdt is None else t.to(self.cdt)).contiguous()
         _, rows, h, d = t.shape
         if h != self.heads:
             raise ValueError(f"expected {self.heads} heads, got {h}")
         send = self._buf(name + ".s", (rows * h, d), t)
-        pos = 0
-        for j in range(w):                                                  # chunk j = rank j's heads of my rows
-            n = rows * self.heads_of[j]
-            send[pos:pos + n].view(rows, self.heads_of[j], d).copy_(t[0][:, self.head_off[j]:self.head_off[j] + self.heads_of[j]])
-            pos += n
+        torch.index_select(t.view(rows * h, d), 0, self._perms(t.device)[0], out=send)
         mine = self.heads_of[sp.rank]
         recv = self._buf(name + ".r", (sp.total_rows * mine, d), t)
         work = dist.all_to_all_single(recv, send, output_split_sizes=[r * mine for r in self.rows_of],
@@ -345,7 +353,7 @@ class UnevenUlyssesAttention(UlyssesAttention):
         self._pending[name] = (recv.view(sp.total_rows, mine, d), work)
 
     def __call__(self, q, k, v):
-        sp, w = self.sp, self.sp.world
+        sp = self.sp
         dtype = q.dtype
         for name, t in (("q", q), ("k", k), ("v", v)):
             if name not in self._pending:
@@ -356,13 +364,8 @@ class UnevenUlyssesAttention(UlyssesAttention):
         recv = self._buf("o.r", (rows * self.heads, d), o)
         dist.all_to_all_single(recv, o.view(sp.total_rows * mine, d), output_split_sizes=[rows * c for c in self.heads_of],
                                input_split_sizes=[r * mine for r in self.rows_of], group=sp.group)
-        out = torch.empty(1, rows, self.heads, d, dtype=o.dtype, device=o.device)
-        pos = 0
-        for s_ in range(w):                                                 # chunk s = rank s's heads of my rows
-            n = rows * self.heads_of[s_]
-            out[0][:, self.head_off[s_]:self.head_off[s_] + self.heads_of[s_]].copy_(recv[pos:pos + n].view(rows, self.heads_of[s_], d))
-            pos += n
-        return out.to(dtype)
+        out = torch.index_select(recv, 0, self._perms(o.device)[1])      # chunk order -> [rows, H] order
+        return out.view(1, rows, self.heads, d).to(dtype)
 
 
 class SequenceParallel:
@@ -380,11 +383,12 @@ class SequenceParallel:
         if mode not in ("auto", "allgather", "ulysses"):
             raise ValueError(f"unknown sequence-parallel mode {mode!r}")
         if mode == "auto":
-            # measured on B200 (profiles/r01_bench_*): at N=2 the all-gather mode is faster (shape A 75.8 vs 80.7 ms/step: equal
-            # bytes, but its exchanges hide under the Q projection while Ulysses has the output exchange and four slab
-            # permutes on the critical path); at N=8 Ulysses is (shape B 286.5 vs 346.0 ms/step: 4x fewer bytes and no
-            # rank repeats the full-sequence K preparation).  N=4 has not been measured yet and stays on all-gather.
-            return "ulysses" if self.world >= 8 and heads % self.world == 0 else "allgather"
+            # measured on B200 (profiles/r01_bench_*, r02_bench_n{2,8}*): at N=2 the all-gather mode is faster (shape A 57.6 vs
+            # 64.5 ms/step: its exchanges hide under the V / Q projections while the all-to-all mode has the output exchange
+            # and the slab permutes on the critical path); at N=8 the all-to-all mode is (shape A, 12 heads -> uneven split
+            # 2,2,2,2,1,1,1,1: 26.4 vs 30.4 ms/step; shape B, 40 heads: 251.8 ms/step, 6.5x one GPU): 4x fewer bytes and no
+            # per-rank work that grows with the full sequence.  N=4 has not been measured and stays on all-gather.
+            return "ulysses" if self.world >= 8 and heads >= self.world else "allgather"
         if mode == "ulysses" and heads < self.world:
             raise ValueError(f"mode 'ulysses' needs at least one head per rank (heads={heads}, world={self.world})")
         return mode
@@ -393,7 +397,7 @@ class SequenceParallel:
         """Replace every block's attention callable by the sequence-parallel one (the reference seam is
         `WanSelfAttention.attn_op.local_attn`, inference/modify_model.py:48-52).  Returns the mode used:
         "allgather" (K/V all-gather + moment all-reduce, any head count) or "ulysses" (head<->sequence all-to-all; with
-        heads % world != 0 the uneven variant, opt-in only)."""
+        heads % world != 0 the uneven-split variant)."""
         used = None
         for blk in model.blocks:
             used = self.pick_mode(blk.heads, mode)
