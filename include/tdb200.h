@@ -142,6 +142,11 @@ int tdb200_rope_interleaved(const void* x, int dtype, const float* angles, void*
                             void* stream);
 int tdb200_rms_norm_rope(const void* x, int dtype, const float* w, const float* angles, void* y, int64_t l, int64_t h,
                          int64_t d, float eps, void* stream);
+/* rms_norm_rope with the rotation read from a table cos_sin [l, d/2, 2] fp32 = (cos a, sin a) of the same angles (the reference
+ * precomputes its complex `freqs` once per call as well, wan2pt1.py:111-137,156-178): one table serves every head, projection
+ * and layer of a denoise step, and the kernel carries no range reduction / sin / cos work. */
+int tdb200_rms_norm_rope_table(const void* x, int dtype, const float* w, const float* cos_sin, void* y, int64_t l, int64_t h,
+                               int64_t d, float eps, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * a7-a10. SLA / SageSLA.  q, k, v, out are [b, l, h, d] contiguous 16-bit (the layout the module is

@@ -144,3 +144,32 @@ def test_residual_with_fused_stats_equals_the_two_pass_path(cuda, m, n, gated):
     torch.cuda.synchronize()
     assert torch.equal(out_a.view(torch.int16), out_b.view(torch.int16))
     assert torch.equal(s_a, s_b) and torch.equal(q_a, q_b)
+
+
+def test_rmsnorm_rope_table_and_in_kernel_sincos_agree_and_the_table_follows_the_angles(cuda, monkeypatch):
+    """ops.rmsnorm_rope reads (cos, sin) from a table cached per angle tensor (tdb200_rms_norm_rope_table); TDB200_ROPE_TABLE=0
+    evaluates sin/cos in the kernel.  Both sit within the fused-RoPE tolerance of the oracle; an in-place change of the angle
+    tensor or a new tensor must not be served a stale table."""
+    import turbodiffusion_b200.ops as ops
+    from turbodiffusion_b200.ops import core as C
+    h, d, (t, hh, ww) = 12, 128, (3, 6, 10)
+    l = t * hh * ww
+    ang = O.wan_rope_angles(t, hh, ww, d)
+    x = _x(l, h * d, 4)
+    w = torch.rand(h * d, generator=torch.Generator().manual_seed(17)) + 0.5
+    ref = O.rms_norm_rope(x.reshape(l, h, d), w, ang, 1e-6)
+    ang_dev = ang.to(cuda)
+    outs = {}
+    for table in (True, False):
+        monkeypatch.setattr(C, "ROPE_TABLE", table)
+        outs[table] = ops.rmsnorm_rope(x.to(cuda), w.to(cuda), ang_dev, 1e-6, h).cpu().reshape(l, h, d)
+        frac, worst = _ulp_report(outs[table], ref)
+        assert worst <= 2.0 and frac < 5e-3, (table, frac, worst)
+    assert (outs[True] != outs[False]).float().mean().item() < 5e-3
+    monkeypatch.setattr(C, "ROPE_TABLE", True)
+    ang_dev.mul_(0.5)                                     # in place: the cached table is stale now
+    got = ops.rmsnorm_rope(x.to(cuda), w.to(cuda), ang_dev, 1e-6, h).cpu().reshape(l, h, d)
+    frac, worst = _ulp_report(got, O.rms_norm_rope(x.reshape(l, h, d), w, ang * 0.5, 1e-6))
+    assert worst <= 2.0 and frac < 5e-3, (frac, worst)
+    got = ops.rmsnorm_rope(x.to(cuda), w.to(cuda), torch.zeros_like(ang_dev), 1e-6, h).cpu()     # zero angles: identity rotation
+    assert torch.equal(got, ops.fast_rmsnorm(x.to(cuda), w.to(cuda), 1e-6).cpu())

@@ -45,6 +45,8 @@ for slot in range(2):
     per_iter = (tt[1:, 0] - tt[:-1, 0]).float()
     print(json.dumps({"slot": slot, "iter_cycles_median": per_iter.median().item(), "iter_cycles_mean": per_iter.mean().item(),
                       "phase_median": {n: d[5:45, i].median().item() for i, n in enumerate(names)},
+                      "wait_S_next+ld_issue_median": (tt[5:45, 7] - tt[5:45, 4]).float().median().item(),
+                      "wait_PV_prev_median": (tt[5:45, 5] - tt[5:45, 7]).float().median().item(),
                       "loop_total": int(t[slot, 63, 7] - tt[0, 0]),
                       "tile_marks_clk_from_entry": {n: int(t[slot, 62, i] - t[slot, 62, 0]) for i, n in
                                                     enumerate(["entry", "first_S", "loop_exit", "phi_published", "OL_ready", "stores_issued"])}}))

@@ -90,7 +90,7 @@ __device__ __forceinline__ void rope_sincos(float x, float* sn, float* cs) {
 }
 
 enum NormKind { kRms = 0, kLayer = 1 };
-enum PostKind { kPostNone = 0, kPostModulate = 1, kPostRope = 2, kPostStatsOnly = 3 };
+enum PostKind { kPostNone = 0, kPostModulate = 1, kPostRope = 2, kPostStatsOnly = 3, kPostRopeTable = 4 };
 
 struct RowParams {
   const void* x;
@@ -99,7 +99,7 @@ struct RowParams {
   const float* b;       // affine bias or NULL
   const float* scale;   // modulation scale (1 + scale applied) or NULL
   const float* shift;   // modulation shift
-  const float* angles;  // RoPE angles [rows, d/2]
+  const float* angles;  // RoPE angles [rows, d/2]; kPostRopeTable: (cos, sin) pairs [rows, d/2, 2]
   float* stats;         // [2*m] mean, rstd (kPostStatsOnly)
   int64_t m;
   int n;
@@ -247,6 +247,19 @@ __global__ void __launch_bounds__(kThreads) row_norm_kernel(RowParams p) {
           const float x0 = Chunk<T>::round(f[j]), x1 = Chunk<T>::round(f[j + 1]);  // rope input is the T-cast norm
           f[j] = __fsub_rn(__fmul_rn(x0, cs), __fmul_rn(x1, sn));
           f[j + 1] = __fadd_rn(__fmul_rn(x0, sn), __fmul_rn(x1, cs));
+        }
+      }
+      if (kPost == kPostRopeTable) {
+        // the same rotation with (cos, sin) read from a table built once per angle tensor: every head of a row and every
+        // layer / projection of a step reuse the same 64 pairs, so the table lines stay in L1/L2 and the kernel keeps no
+        // range reduction or MUFU work (the sincos form is issue-bound: profiles/r02_ncu_prologue.txt)
+        float cs[E];
+        load_params<E>(p.angles + (row * (p.d >> 1) + ((col % p.d) >> 1)) * 2, cs);
+#pragma unroll
+        for (int j = 0; j < E; j += 2) {
+          const float x0 = Chunk<T>::round(f[j]), x1 = Chunk<T>::round(f[j + 1]);
+          f[j] = __fsub_rn(__fmul_rn(x0, cs[j]), __fmul_rn(x1, cs[j + 1]));
+          f[j + 1] = __fadd_rn(__fmul_rn(x0, cs[j + 1]), __fmul_rn(x1, cs[j]));
         }
       }
       stg_v4(yr + col, Chunk<T>::pack(f));
@@ -549,6 +562,17 @@ extern "C" int tdb200_rms_norm_rope(const void* x, int dtype, const float* w, co
   if (l == 0) return TDB200_OK;
   RowParams p{x, y, w, nullptr, nullptr, nullptr, angles, nullptr, l, static_cast<int>(h * d), static_cast<int>(d), eps, nullptr, nullptr};
   return dispatch16<kRms, kPostRope>(dtype, p, static_cast<cudaStream_t>(stream), "rms_norm_rope");
+}
+
+extern "C" int tdb200_rms_norm_rope_table(const void* x, int dtype, const float* w, const float* cos_sin, void* y, int64_t l,
+                                          int64_t h, int64_t d, float eps, void* stream) {
+  using namespace tdb;
+  if (int rc = check_rows("rms_norm_rope_table", x, y, l, h * d, 8)) return rc;
+  if (!cos_sin || !w || d % 8 != 0 || !aligned16(cos_sin))
+    return fail(TDB200_ERR_INVALID_ARG, "rms_norm_rope_table: null / misaligned pointer or d %% 8 != 0");
+  if (l == 0) return TDB200_OK;
+  RowParams p{x, y, w, nullptr, nullptr, nullptr, cos_sin, nullptr, l, static_cast<int>(h * d), static_cast<int>(d), eps, nullptr, nullptr};
+  return dispatch16<kRms, kPostRopeTable>(dtype, p, static_cast<cudaStream_t>(stream), "rms_norm_rope_table");
 }
 
 extern "C" int tdb200_gate_residual_stats(const void* x, const void* y, const float* gate, void* out, float* row_stats,

@@ -55,7 +55,8 @@ constexpr float kRescaleThreshold = 8.0f;         // log2 domain
 
 // Optional phase trace (diagnostics): when set through tdb200_debug_set_attn_trace(), lane 0 of softmax warp 0 of CTAs
 // (x == 1, y == 0, z == 0) and (x == 3, ...) records clock64() at the phase boundaries of its first 64 iterations:
-// trace[slot][j][0..6] = loop top, S ready, S in registers, max/vote done, exps done, P buffer free, P published.
+// trace[slot][j][0..6] = loop top, S ready, S in registers, max/vote done, exps done, P buffer free, P published;
+// [7] = S(j+1) ready and its tcgen05.ld issued (between 4 and 5).
 __device__ long long* g_attn_trace = nullptr;
 #define TDB_TRACE(slot_ok, j, k)                                                       \
   do {                                                                                 \
@@ -409,6 +410,7 @@ sla_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q8, const __grid_co
         tmem_ld_x32(tn, s0);
         tmem_ld_x32(tn + 32, s1);
       }
+      TDB_TRACE(tracing, j, 7);
 
       // ---- P row -> tensor memory: 32 packed columns over the S buffer this block was read from.  The wait for P.V(j-1)
       //      stays: the parity waits on kBarPvDone / kBarPEmpty are only unambiguous while the softmax warps run at most

@@ -6,6 +6,8 @@ unchanged.  Additional fused entry points (one HBM pass instead of several) sit 
 """
 from __future__ import annotations
 
+import os
+import weakref
 from typing import Optional, Tuple
 
 import torch
@@ -303,14 +305,39 @@ def rope_interleaved(x: torch.Tensor, angles: torch.Tensor) -> torch.Tensor:
     return y
 
 
+_ROPE_TABLES = {}   # id(angles) -> (weakref to the angle tensor, its _version, (cos, sin) table [L, D/2, 2] fp32)
+ROPE_TABLE = os.environ.get("TDB200_ROPE_TABLE", "1") != "0"   # "0": evaluate sin/cos inside the kernel (A/B timing)
+
+
+def rope_cos_sin(angles: torch.Tensor) -> torch.Tensor:
+    """(cos, sin) of an angle tensor [L, D/2] as one fp32 table [L, D/2, 2], built once per tensor (and per in-place version of
+    it) and reused by every rmsnorm_rope call that is handed the same angles: all heads, q and k, every layer of a step."""
+    key = id(angles)
+    hit = _ROPE_TABLES.get(key)
+    if hit is not None and hit[0]() is angles and hit[1] == angles._version:
+        return hit[2]
+    if len(_ROPE_TABLES) >= 16:
+        _ROPE_TABLES.clear()
+    a = angles.detach().float()
+    table = torch.stack((torch.cos(a), torch.sin(a)), dim=-1).contiguous()
+    _ROPE_TABLES[key] = (weakref.ref(angles), angles._version, table)
+    return table
+
+
 def rmsnorm_rope(x: torch.Tensor, w: torch.Tensor, angles: torch.Tensor, eps: float, heads: int) -> torch.Tensor:
     """rope_apply(norm_q(x).view(L, H, D), freqs) in one pass; x [L, H*D]."""
     require_cuda(x, w, angles)
     xc = x.contiguous()
     l, hd = xc.shape
     w = _f32(w, hd, "rmsnorm_rope weight")
-    angles = _f32(angles, l * (hd // heads // 2), "rmsnorm_rope angles")
     y = torch.empty_like(xc)
+    if ROPE_TABLE:
+        if angles.numel() != l * (hd // heads // 2):
+            raise ValueError("rmsnorm_rope angles: expected [L, head_dim/2]")
+        check(lib().tdb200_rms_norm_rope_table(ptr(xc), DTYPE_TAG[x.dtype], ptr(w), ptr(rope_cos_sin(angles)), ptr(y), l, heads,
+                                               hd // heads, float(eps), stream_ptr(x.device)), "rmsnorm_rope")
+        return y
+    angles = _f32(angles, l * (hd // heads // 2), "rmsnorm_rope angles")
     check(lib().tdb200_rms_norm_rope(ptr(xc), DTYPE_TAG[x.dtype], ptr(w), ptr(angles), ptr(y), l, heads, hd // heads,
                                      float(eps), stream_ptr(x.device)), "rmsnorm_rope")
     return y
