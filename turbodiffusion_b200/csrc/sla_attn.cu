@@ -412,10 +412,12 @@ sla_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q8, const __grid_co
       }
       TDB_TRACE(tracing, j, 7);
 
-      // ---- P row -> tensor memory: 32 packed columns over the S buffer this block was read from.  The wait for P.V(j-1)
-      //      stays: the parity waits on kBarPvDone / kBarPEmpty are only unambiguous while the softmax warps run at most
-      //      one P.V ahead of the tensor pipe (two ahead would alias the phase bit in the lazy-rescale wait above).
-      mbar_wait(&bars[kBarPEmpty], (j & 1) ^ 1);
+      // ---- P row -> tensor memory: 32 packed columns over the S buffer this block was read from.  The softmax warps may run
+      //      at most one P.V ahead of the tensor pipe (two ahead would alias the phase bit in the lazy-rescale wait above).
+      //      S(j+1) full - waited for just above - already implies that: its tcgen05.commit was issued after P.V(j-1)'s MMAs,
+      //      and a commit completes only when every earlier MMA of the issuing thread has.  Only the last block, which has no
+      //      next S tile, polls the P.V barrier itself (a poll costs ~65 clk even when the phase is long complete).
+      if (j + 1 >= T_blocks) mbar_wait(&bars[kBarPEmpty], (j & 1) ^ 1);
       TDB_TRACE(tracing, j, 5);
       tmem_st_x32(tmem_base + lane_addr + kColS + uint32_t(st) * BLKK, pw);
       tmem_st_wait();
