@@ -212,6 +212,8 @@ def fast_rmsnorm(x: torch.Tensor, w: torch.Tensor, eps: float) -> torch.Tensor:
     if x2 is None:  # fp32 input: the reference entry point
         return rmsnorm(x.float().contiguous(), w, eps).to(x.dtype)
     y = torch.empty_like(x2)
+    if x2.numel() == 0:          # empty batch: nothing to launch (an empty tensor has no data pointer to hand to the C ABI)
+        return y.reshape(x.shape)
     w = _f32(w, x2.shape[1], "fast_rmsnorm weight")
     check(lib().tdb200_rms_norm(ptr(x2), DTYPE_TAG[x.dtype], ptr(w), ptr(y), x2.shape[0], x2.shape[1],
                                 float(eps), stream_ptr(x.device)), "fast_rmsnorm")
@@ -224,6 +226,8 @@ def fast_layernorm(x, w, b, eps) -> torch.Tensor:
     if x2 is None:
         return layernorm(x.float().contiguous(), w, b, eps, w is not None).to(x.dtype)
     y = torch.empty_like(x2)
+    if x2.numel() == 0:
+        return y.reshape(x.shape)
     w, b = _f32(w, x2.shape[1], "fast_layernorm weight"), _f32(b, x2.shape[1], "fast_layernorm bias")
     check(lib().tdb200_layer_norm(ptr(x2), DTYPE_TAG[x.dtype], ptr(w), ptr(b), ptr(y), x2.shape[0], x2.shape[1], float(eps),
                                   stream_ptr(x.device)), "fast_layernorm")

@@ -36,6 +36,8 @@ def quant_cuda(x: torch.Tensor, out_q: Optional[torch.Tensor] = None,
         out_q = torch.empty((m, k), dtype=torch.int8, device=x.device)
     if out_s is None:
         out_s = torch.empty((_cdiv(m, 128), _cdiv(k, 128)), dtype=torch.float32, device=x.device)
+    if m == 0 or k == 0:         # empty batch: nothing to launch (an empty tensor has no data pointer to hand to the C ABI)
+        return out_q, out_s
     check(lib().tdb200_quant_int8_block128(ptr(x), DTYPE_TAG[x.dtype], m, k, ptr(out_q), ptr(out_s),
                                            stream_ptr(x.device)), "quant_cuda")
     return out_q, out_s
@@ -74,6 +76,8 @@ def _gemm_impl(a_q, a_s, b_q, b_s, c, bias, epilogue: int = 0):
     if bias is not None and bias.dtype != c.dtype:
         bias = bias.to(c.dtype)
     m, n, k = a_q.size(0), b_q.size(0), b_q.size(1)  # gemm.cu:37-39
+    if m == 0 or n == 0:
+        return
     check(lib().tdb200_gemm_w8a8_ex(ptr(a_q), ptr(a_s), ptr(b_q), ptr(b_s), ptr(bias), ptr(c), DTYPE_TAG[c.dtype], m,
                                     n, k, epilogue, stream_ptr(c.device)), "gemm_cuda")
 
