@@ -202,4 +202,5 @@ def test_pick_mode():
         sp.pick_mode(4, "ulysses")                             # fewer heads than ranks
     assert SequenceParallel(32760, world=1, rank=0).pick_mode(12) == "allgather"
     assert SequenceParallel(32760, world=2, rank=0).pick_mode(12) == "allgather"   # measured faster at N=2
+    assert SequenceParallel(32760, world=4, rank=0).pick_mode(12) == "ulysses"     # measured faster from N=4 up
     assert SequenceParallel(32760, world=2, rank=0).pick_mode(12, "ulysses") == "ulysses"

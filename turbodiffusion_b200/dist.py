@@ -383,12 +383,12 @@ class SequenceParallel:
         if mode not in ("auto", "allgather", "ulysses"):
             raise ValueError(f"unknown sequence-parallel mode {mode!r}")
         if mode == "auto":
-            # measured on B200 (profiles/r01_bench_*, r02_bench_n{2,8}*): at N=2 the all-gather mode is faster (shape A 57.6 vs
-            # 64.5 ms/step: its exchanges hide under the V / Q projections while the all-to-all mode has the output exchange
-            # and the slab permutes on the critical path); at N=8 the all-to-all mode is (shape A, 12 heads -> uneven split
-            # 2,2,2,2,1,1,1,1: 26.4 vs 30.4 ms/step; shape B, 40 heads: 251.8 ms/step, 6.5x one GPU): 4x fewer bytes and no
-            # per-rank work that grows with the full sequence.  N=4 has not been measured and stays on all-gather.
-            return "ulysses" if self.world >= 8 and heads >= self.world else "allgather"
+            # measured on B200, shape A, ms/step all-gather vs all-to-all (profiles/r02_bench_n{2,4,8}*): N=2 57.6 vs 64.5 (the
+            # all-gather's exchanges hide under the V / Q projections; the all-to-all has the output exchange and the slab
+            # permutes on the critical path), N=4 37.8 vs 35.5, N=8 30.4 vs 26.4 (12 heads -> uneven split 2,2,2,2,1,1,1,1);
+            # shape B at N=8 (40 heads): 251.8 ms/step, 6.5x one GPU.  From N=4 up the all-to-all moves N/2 times fewer bytes
+            # and has no per-rank work that grows with the full sequence.
+            return "ulysses" if self.world >= 4 and heads >= self.world else "allgather"
         if mode == "ulysses" and heads < self.world:
             raise ValueError(f"mode 'ulysses' needs at least one head per rank (heads={heads}, world={self.world})")
         return mode
