@@ -181,6 +181,9 @@ int tdb200_sla_linear_moments(const void* k, const void* v, int dtype, int64_t b
  * 64 or 128 (kv [b,h,d,d], ksum [b,h,d]). */
 int tdb200_sla_linear_moments_ex(const void* k, const void* v, int dtype, int64_t b, int64_t l, int64_t h, int64_t d,
                                  int feature, float* kv, float* ksum, void* stream);
+/* kvw [bh,d,d] T = T(proj_w [d,d] . kv [bh,d,d]): folds proj_l's weight (SLA/core.py:246 `self.proj_l(o_l)`) into the moment
+ * matrix so the fused kernel applies it with its last MMA; fp32 FMA chain over d_v. */
+int tdb200_sla_project_moments(const float* proj_w, const float* kv, int dtype, int64_t bh, int64_t d, void* kvw, void* stream);
 int tdb200_sla_attn_fwd(const int8_t* q_i8, const float* q_scale, const int8_t* k_i8, const float* k_scale,
                         const void* v, const void* q, int dtype, const int32_t* lut, int64_t topk, const void* kvw,
                         const float* ksum, const float* proj_b, void* out, int64_t b, int64_t l, int64_t lk,

@@ -187,6 +187,19 @@ def test_uneven_ulysses_attention_gloo_world2(tmp_path, l, h):
     assert res["stats"]["rel_l2"] < 1e-4, res
 
 
+def test_uneven_ulysses_attention_gloo_world8_twelve_heads(tmp_path):
+    """The N = 8 default for Wan-1.3B: 12 heads over 8 ranks (2,2,2,2,1,1,1,1), sixteen 128-row blocks over 8 ranks (the last rank
+    holds the ragged tail), the gather-kernel reordering on both sides of the exchange."""
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    out = str(tmp_path / "ul8.pt")
+    mp.spawn(_worker, args=(8, port, 2000, 12, 64, 0.3, out, "ulysses"), nprocs=8, join=True)
+    res = torch.load(out)
+    assert res["stats"]["rel_l2"] < 1e-4, res
+
+
 def test_split_heads():
     assert split_heads(12, 8) == ([2, 2, 2, 2, 1, 1, 1, 1], [0, 2, 4, 6, 8, 9, 10, 11])
     assert split_heads(40, 8) == ([5] * 8, list(range(0, 40, 5)))

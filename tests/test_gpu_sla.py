@@ -458,3 +458,19 @@ def test_attention_reads_sequence_major_int8_keys(cuda):
     prep.k_i8, prep.k_seq_major = k_seq, True
     got = attn_fwd(prep, v_pad, q, lut, topk, kvw, ksum, pb, d ** -0.5, lk=l)
     assert torch.equal(got, ref)
+
+
+@pytest.mark.parametrize("d,h,dtype", [(128, 3, torch.bfloat16), (64, 4, torch.float16)])
+def test_project_moments_equals_the_matmul(cuda, d, h, dtype):
+    """kvw = T(proj_w . kv) (one launch) against torch.matmul in fp32 + cast: same values up to the summation order of the fp32
+    chain (a last-place flip of the 16-bit result on a few elements)."""
+    from turbodiffusion_b200.SLA.core import project_moments
+    g = torch.Generator().manual_seed(d + h)
+    w = (torch.randn(d, d, generator=g) * 0.05).to(cuda)
+    kv = (torch.randn(2, h, d, d, generator=g) * 3).to(cuda)
+    got = project_moments(w, kv, dtype)
+    ref = torch.matmul(w.double(), kv.double())
+    assert got.shape == (2, h, d, d) and got.dtype == dtype
+    err = (got.double() - ref).abs()
+    ulp = ref.abs().clamp_min(1e-3) * (2.0 ** -8 if dtype == torch.bfloat16 else 2.0 ** -11)
+    assert (err <= ulp).all(), (err / ulp).max().item()     # within one rounding of T of the exact product

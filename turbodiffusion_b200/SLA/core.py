@@ -29,11 +29,22 @@ def linear_moments(k: torch.Tensor, v: torch.Tensor, feature: int = 0):
     """kv [B,H,D(v),D(k)] fp32, ksum [B,H,D] fp32 of the local keys (accumulated: add shards / all-reduce).  D in {64, 128};
     `feature`: 0 softmax over D, 1 elu+1, 2 relu."""
     b, l, h, d = k.shape
-    kv = torch.zeros(b, h, d, d, dtype=torch.float32, device=k.device)
-    ksum = torch.zeros(b, h, d, dtype=torch.float32, device=k.device)
+    buf = torch.zeros(b * h * d * (d + 1), dtype=torch.float32, device=k.device)        # one fill for both accumulators
+    kv, ksum = buf[: b * h * d * d].view(b, h, d, d), buf[b * h * d * d:].view(b, h, d)
     check(lib().tdb200_sla_linear_moments_ex(ptr(k), ptr(v), DTYPE_TAG[k.dtype], b, l, h, d, feature, ptr(kv), ptr(ksum),
                                              stream_ptr(k.device)), "sla_linear_moments")
     return kv, ksum
+
+
+def project_moments(proj_w: torch.Tensor, kv: torch.Tensor, dtype) -> torch.Tensor:
+    """kvw [B,H,D_out,D_k] = T(proj_w . kv): proj_l's weight folded into the moment matrix (the fused kernel's last MMA)."""
+    b, h, d, _ = kv.shape
+    w = proj_w if (proj_w.dtype == torch.float32 and proj_w.is_contiguous()) else proj_w.float().contiguous()
+    assert kv.dtype == torch.float32 and kv.is_contiguous() and w.shape == (d, d)
+    out = torch.empty(b, h, d, d, dtype=dtype, device=kv.device)
+    check(lib().tdb200_sla_project_moments(ptr(w), ptr(kv), DTYPE_TAG[dtype], b * h, d, ptr(out), stream_ptr(kv.device)),
+          "sla_project_moments")
+    return out
 
 
 ATTN_IMPL = os.environ.get("TDB200_ATTN_IMPL", "v1")  # "v1": one CTA per query block; "v2": persistent kernel (measured slower, see DESIGN)
@@ -125,7 +136,7 @@ class _SLABase(nn.Module):
             self._keep_selection.update(lut=lut, sparse_map=sparse_map, topk=real_topk)
         kv, ksum = linear_moments(k, v, self.feature)
         # proj_l folded into the moments: (phi(q) KV / den) W^T + b == phi(q) (W KV^T)^T / den + b ; kv is [dv, dk]
-        kvw = torch.matmul(self.proj_l.weight.float(), kv).to(self.dtype).contiguous()  # [B,H,d_out,d_k]
+        kvw = project_moments(self.proj_l.weight, kv, self.dtype)  # [B,H,d_out,d_k]
         # 128-wide heads with the softmax map run the one-CTA-per-query-block kernel (faster); 64-wide heads and the
         # elu / relu maps run the persistent kernel, which has native 64-wide tiles and the feature-map switch
         impl = ATTN_IMPL if (d == 128 and self.feature == 0) else "v2"

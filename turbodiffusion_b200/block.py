@@ -117,13 +117,15 @@ class WanBlockB200:
 
     # -- forward -------------------------------------------------------------------------------------------------
     def forward(self, x: torch.Tensor, e0: torch.Tensor, angles: torch.Tensor, context: torch.Tensor,
-                stats: Optional[torch.Tensor] = None, want_stats: bool = False):
+                stats: Optional[torch.Tensor] = None, want_stats: bool = False, e: Optional[torch.Tensor] = None):
         """x [L, dim] 16-bit, e0 [6, dim] fp32 (time modulation), angles [L, head_dim/2] fp32, context [Lc, dim].
         `stats`: LayerNorm row statistics of x if the producer of x already computed them (the previous block's last
-        residual kernel does); with want_stats=True returns (x_out, stats_of_x_out) for the next block."""
+        residual kernel does); with want_stats=True returns (x_out, stats_of_x_out) for the next block.  `e`: this block's
+        `modulation + e0` [6, dim] fp32 if the caller already formed it (WanHotPath adds all blocks' tables in one launch)."""
         sd, dim, h, d, eps = self.sd, self.dim, self.heads, self.head_dim, self.eps
         l = x.shape[0]
-        e = (sd["modulation"][0] + e0).contiguous()  # [6, dim] fp32 (wan2pt1.py:400)
+        if e is None:
+            e = (sd["modulation"][0] + e0).contiguous()  # [6, dim] fp32 (wan2pt1.py:400)
 
         # ---- self-attention (wan2pt1.py:404, 251-274)
         if stats is None:
@@ -195,13 +197,17 @@ class WanHotPath:
         self.dim, self.heads, self.dtype = dim, heads, dtype
         self.blocks = [WanBlockB200(random_block_state(dim, ffn_dim, heads, seed + i, device, dtype), dim, heads, topk=topk)
                        for i in range(num_layers)]
+        self._mods = None
 
     def step(self, x, e0, angles, context):
         stats = None
         last = len(self.blocks) - 1
+        if self._mods is None:   # every block's modulation table, stacked once: `modulation + e0` is then one launch per step
+            self._mods = torch.stack([blk.sd["modulation"][0] for blk in self.blocks]).contiguous()
+        e_all = self._mods + e0
         for i, blk in enumerate(self.blocks):
             if i < last:  # the block's final residual kernel also emits the next block's LayerNorm statistics
-                x, stats = blk(x, e0, angles, context, stats, want_stats=True)
+                x, stats = blk(x, e0, angles, context, stats, want_stats=True, e=e_all[i])
             else:
-                x = blk(x, e0, angles, context, stats)
+                x = blk(x, e0, angles, context, stats, e=e_all[i])
         return x

@@ -326,3 +326,53 @@ extern "C" int tdb200_sla_linear_moments_ex(const void* k, const void* v, int dt
                                             int64_t d, int feature, float* kv, float* ksum, void* stream) {
   return moments_impl(k, v, dtype, b, l, h, d, feature, kv, ksum, stream);
 }
+
+// ---- kvw = T(proj_w . kv): the linear branch's output projection folded into the moment matrix (SLA/core.py:243-253:
+// proj_l(phi(q) kv / den) == phi(q) (proj_w kv)^T / den + b), one launch instead of a library sgemm plus casts.
+//   proj_w [d_out, d_v] fp32, kv [bh, d_v, d_k] fp32  ->  kvw [bh, d_out, d_k] T;  fp32 FMA chain over d_v in ascending order.
+namespace {
+template <typename T, int D>
+__global__ void __launch_bounds__(D) project_moments_kernel(const float* __restrict__ w, const float* __restrict__ kv,
+                                                            T* __restrict__ out) {
+  constexpr int kRows = 32;                      // output rows (d_out) per CTA
+  __shared__ float ws[kRows][D];
+  const int bh = blockIdx.x, o0 = blockIdx.y * kRows, k = threadIdx.x;
+  for (int i = threadIdx.x; i < kRows * D; i += D) ws[i / D][i % D] = __ldg(w + int64_t(o0 + i / D) * D + (i % D));
+  __syncthreads();
+  float acc[kRows];
+#pragma unroll
+  for (int i = 0; i < kRows; ++i) acc[i] = 0.f;
+  const float* kvp = kv + int64_t(bh) * D * D + k;
+#pragma unroll 4
+  for (int v = 0; v < D; ++v) {
+    const float x = __ldg(kvp + int64_t(v) * D);
+#pragma unroll
+    for (int i = 0; i < kRows; ++i) acc[i] = fmaf(ws[i][v], x, acc[i]);
+  }
+  T* op = out + (int64_t(bh) * D + o0) * D + k;
+#pragma unroll
+  for (int i = 0; i < kRows; ++i) op[int64_t(i) * D] = static_cast<T>(acc[i]);
+}
+}  // namespace
+
+extern "C" int tdb200_sla_project_moments(const float* proj_w, const float* kv, int dtype, int64_t bh, int64_t d, void* kvw,
+                                          void* stream) {
+  using namespace tdb;
+  if (!proj_w || !kv || !kvw) return fail(TDB200_ERR_INVALID_ARG, "sla_project_moments: null pointer");
+  if (bh <= 0 || bh > 0x7FFFFFFF) return fail(TDB200_ERR_INVALID_ARG, "sla_project_moments: bad shape");
+  if (d != 64 && d != 128) return fail(TDB200_ERR_UNSUPPORTED, "sla_project_moments: head dim %lld (64 or 128)", (long long)d);
+  if (int rc = require_sm100()) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  dim3 grid(static_cast<unsigned>(bh), static_cast<unsigned>(d / 32));
+#define TDB_PM(T, D) project_moments_kernel<T, D><<<grid, D, 0, st>>>(proj_w, kv, static_cast<T*>(kvw)); return check_launch("project_moments_kernel")
+  if (dtype == TDB200_DTYPE_BF16) {
+    if (d == 128) { TDB_PM(__nv_bfloat16, 128); }
+    TDB_PM(__nv_bfloat16, 64);
+  }
+  if (dtype == TDB200_DTYPE_FP16) {
+    if (d == 128) { TDB_PM(__half, 128); }
+    TDB_PM(__half, 64);
+  }
+#undef TDB_PM
+  return fail(TDB200_ERR_UNSUPPORTED, "sla_project_moments: dtype tag %d", dtype);
+}

@@ -64,14 +64,14 @@ class GpuPrimitives:
         return quant_q_only(q)
 
     def attention(self, q, k_full, v_full, lk, kv, ksum, qprep=None):
-        from .SLA.core import attn_fwd
+        from .SLA.core import attn_fwd, project_moments
         from .SLA.utils import block_map_from_pools, quant_k_into, quant_q_only
         sla = self.sla
         d = q.shape[-1]
         prep = quant_k_into(qprep if qprep is not None else quant_q_only(q), k_full, lk)
         topk = min(prep.nblk, int(sla.topk * prep.nblk))
         _, lut = block_map_from_pools(prep.q_pool, prep.k_pool, topk)
-        kvw = torch.matmul(sla.proj_l.weight.float(), kv).to(q.dtype).contiguous()
+        kvw = project_moments(sla.proj_l.weight, kv, q.dtype)
         return attn_fwd(prep, v_full, q, lut, topk, kvw, ksum, sla.proj_l.bias.float().contiguous(), d ** -0.5, lk=lk)
 
     def moments(self, k_local, v_local):
@@ -92,7 +92,7 @@ class GpuPrimitives:
         return quant_k_seq(k_local, kmean, k_i8_out)
 
     def attention_i8(self, q, qprep, k_i8_full, k_scale, k_pool, kmean, v_full, lk, kv, ksum):
-        from .SLA.core import attn_fwd
+        from .SLA.core import attn_fwd, project_moments
         from .SLA.utils import block_map_from_pools, cdiv as _cdiv, quant_q_only
         sla = self.sla
         d = q.shape[-1]
@@ -101,7 +101,7 @@ class GpuPrimitives:
         prep.nblk, prep.k_seq_major = _cdiv(lk, 64), True
         topk = min(prep.nblk, int(sla.topk * prep.nblk))
         _, lut = block_map_from_pools(prep.q_pool, prep.k_pool, topk)
-        kvw = torch.matmul(sla.proj_l.weight.float(), kv).to(q.dtype).contiguous()
+        kvw = project_moments(sla.proj_l.weight, kv, q.dtype)
         return attn_fwd(prep, v_full, q, lut, topk, kvw, ksum, sla.proj_l.bias.float().contiguous(), d ** -0.5, lk=lk)
 
 
@@ -181,9 +181,12 @@ class SPAttention:
         v = v.to(cdt).contiguous()
         v_full, wv = self._gather_async("v", v[0], sp.rows_pad)
         kv, ksum = self.prims.moments(k, v)
-        w1 = dist.all_reduce(kv, group=sp.group, async_op=True)
-        w2 = dist.all_reduce(ksum, group=sp.group, async_op=True)
-        self._pending = (kx, v_full.unsqueeze(0), kv, ksum, works + [wv, w1, w2])
+        base = kv._base
+        if base is not None and ksum._base is base and base.is_contiguous() and base.numel() == kv.numel() + ksum.numel():
+            red = [dist.all_reduce(base, group=sp.group, async_op=True)]      # both accumulators live in one buffer: one collective
+        else:
+            red = [dist.all_reduce(kv, group=sp.group, async_op=True), dist.all_reduce(ksum, group=sp.group, async_op=True)]
+        self._pending = (kx, v_full.unsqueeze(0), kv, ksum, works + [wv] + red)
 
     def __call__(self, q, k, v):
         sp = self.sp
@@ -216,7 +219,7 @@ class UlyssesGpuPrims:
         self.sla = sla_module
 
     def attend(self, get_q, get_k, get_v):
-        from .SLA.core import attn_fwd, linear_moments
+        from .SLA.core import attn_fwd, linear_moments, project_moments
         from .SLA.utils import QKPrep, block_map_from_pools, quant_k_into, quant_q_only
         sla = self.sla
         k = get_k()
@@ -232,7 +235,7 @@ class UlyssesGpuPrims:
         _, lut = block_map_from_pools(prep.q_pool, prep.k_pool, topk)
         v = get_v()
         kv, ksum = linear_moments(k, v)
-        kvw = torch.matmul(sla.proj_l.weight.float(), kv).to(q.dtype).contiguous()
+        kvw = project_moments(sla.proj_l.weight, kv, q.dtype)
         return attn_fwd(prep, v, q, lut, topk, kvw, ksum, sla.proj_l.bias.float().contiguous(), d ** -0.5)
 
 
