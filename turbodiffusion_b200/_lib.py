@@ -12,7 +12,7 @@ import torch
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG_DIR, "libtdb200.so")
-if os.environ.get("TDB200_LIB"):   # kernel-variant experiments (tools/gpu_gemm_magic.sh): a differently compiled build of the same ABI
+if os.environ.get("TDB200_LIB"):   # kernel-variant experiments: a differently compiled build of the same ABI (see profiles/r02_gemm_experiments.md, call 21)
     LIB_PATH = os.environ["TDB200_LIB"]
 
 DTYPE_TAG = {torch.bfloat16: 0, torch.float16: 1}
