@@ -266,6 +266,8 @@ int tdb200_selftest_tmem_read(int warps, int iters, int convert, long long* cycl
 /* XU (MUFU) throughput probe: mode 0/1/2 = ex2 f32 / bf16x2 / f16x2, 3/4/5 = tanh f32 / bf16x2 / f16x2; one CTA per SM with
  * `warps` warps, 8 independent chains x `iters` per thread; cycles_per_cta[sm_count]. Diagnostics only. */
 int tdb200_selftest_mufu(int mode, int warps, int iters, long long* cycles_per_cta, float* sink, void* stream);
+/* diagnostics: the exponential pass of the fused attention's softmax warps on register data (variants drop the packing / the row sums) */
+int tdb200_selftest_softmax_exps(int variant, int warps, int iters, long long* cycles_per_cta, float* sink, void* stream);
 
 #ifdef __cplusplus
 }

@@ -66,6 +66,7 @@ _PROTOS = {
     "tdb200_selftest_umma_bf16": [_P, _P, _P, _P],
     "tdb200_selftest_tmem_read": [_I, _I, _I, _P, _P, _P],
     "tdb200_selftest_mufu": [_I, _I, _I, _P, _P, _P],
+    "tdb200_selftest_softmax_exps": [_I, _I, _I, _P, _P, _P],
 }
 _RESTYPES = {"tdb200_last_error": c_char_p}
 

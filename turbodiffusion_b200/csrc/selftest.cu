@@ -224,3 +224,101 @@ extern "C" int tdb200_selftest_mufu(int mode, int warps, int iters, long long* c
   }
   return check_launch("mufu_probe_kernel");
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Softmax inner-loop probe: the exponential pass of sla_attn.cu's softmax warps on register data (64 int32 scores per thread ->
+// magic-add int->float, packed scale FMA, ex2, packed row sums, 16-bit packing), `iters` times, one CTA per SM.
+//   variant 0: the loop as shipped     1: no 16-bit packing     2: no row sums     3: no packing, no sums (IADD + FFMA2 + ex2)
+//   variant 4: one FADD + ex2 per value, nothing else
+// cycles / iters = duration of one block's exponential phase for a warp (the XU floor is 64 ex2 x 8 clk = 512 with one warp per
+// scheduler, `warps` = 4; 1024 with two, `warps` = 8).
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+template <int kVar>
+__global__ void __launch_bounds__(1024, 1) exps_probe_kernel(int iters, long long* cycles, float* sink, float sc, float cbias) {
+  uint32_t s0[32], s1[32];
+#pragma unroll
+  for (int c = 0; c < 32; ++c) {
+    s0[c] = uint32_t(-int(threadIdx.x * 7 + c * 13) % 4096);
+    s1[c] = uint32_t(-int(threadIdx.x * 5 + c * 11) % 4096);
+  }
+  constexpr int kMagicI = 0x4B400000;
+  const float2 sc2 = make_float2(sc, sc);
+  float l_sum = 0.f;
+  uint32_t acc_bits = 0;
+  __syncthreads();
+  const long long t0c = clock64();
+  for (int it = 0; it < iters; ++it) {
+    // the bias of every scale FMA depends on the previous iteration's results: nothing can be hoisted out of the loop
+    const float cb = cbias + static_cast<float>(acc_bits & 1u) * 1e-30f;
+    const float2 cb2 = make_float2(cb, cb);
+    float2 psa = make_float2(0.f, 0.f), psb = psa, psc = psa, psd = psa;
+    uint32_t pw[32];
+#pragma unroll
+    for (int c = 0; c < 32; c += 4) {
+      float2 t0, t1, t2, t3;
+      if (kVar == 4) {   // one scalar add per value instead of the magic add + packed FMA
+        t0 = make_float2(__uint_as_float(s0[c]) + cb, __uint_as_float(s0[c + 1]) + cb);
+        t1 = make_float2(__uint_as_float(s0[c + 2]) + cb, __uint_as_float(s0[c + 3]) + cb);
+        t2 = make_float2(__uint_as_float(s1[c]) + cb, __uint_as_float(s1[c + 1]) + cb);
+        t3 = make_float2(__uint_as_float(s1[c + 2]) + cb, __uint_as_float(s1[c + 3]) + cb);
+      } else {
+        t0 = __ffma2_rn(make_float2(__int_as_float(int(s0[c]) + kMagicI), __int_as_float(int(s0[c + 1]) + kMagicI)), sc2, cb2);
+        t1 = __ffma2_rn(make_float2(__int_as_float(int(s0[c + 2]) + kMagicI), __int_as_float(int(s0[c + 3]) + kMagicI)), sc2, cb2);
+        t2 = __ffma2_rn(make_float2(__int_as_float(int(s1[c]) + kMagicI), __int_as_float(int(s1[c + 1]) + kMagicI)), sc2, cb2);
+        t3 = __ffma2_rn(make_float2(__int_as_float(int(s1[c + 2]) + kMagicI), __int_as_float(int(s1[c + 3]) + kMagicI)), sc2, cb2);
+      }
+      t0.x = fast_exp2(t0.x); t0.y = fast_exp2(t0.y);
+      t1.x = fast_exp2(t1.x); t1.y = fast_exp2(t1.y);
+      t2.x = fast_exp2(t2.x); t2.y = fast_exp2(t2.y);
+      t3.x = fast_exp2(t3.x); t3.y = fast_exp2(t3.y);
+      if (kVar == 0 || kVar == 1) {
+        psa = __fadd2_rn(psa, t0);
+        psb = __fadd2_rn(psb, t1);
+        psc = __fadd2_rn(psc, t2);
+        psd = __fadd2_rn(psd, t3);
+      }
+      if (kVar == 0 || kVar == 2) {
+        pw[c >> 1] = F16Traits<__nv_bfloat16>::pack(t0.x, t0.y);
+        pw[(c >> 1) + 1] = F16Traits<__nv_bfloat16>::pack(t1.x, t1.y);
+        pw[16 + (c >> 1)] = F16Traits<__nv_bfloat16>::pack(t2.x, t2.y);
+        pw[17 + (c >> 1)] = F16Traits<__nv_bfloat16>::pack(t3.x, t3.y);
+      } else {
+        pw[c >> 1] = __float_as_uint(t0.x) ^ __float_as_uint(t0.y);
+        pw[(c >> 1) + 1] = __float_as_uint(t1.x) ^ __float_as_uint(t1.y);
+        pw[16 + (c >> 1)] = __float_as_uint(t2.x) ^ __float_as_uint(t2.y);
+        pw[17 + (c >> 1)] = __float_as_uint(t3.x) ^ __float_as_uint(t3.y);
+      }
+    }
+    const float2 ps2 = __fadd2_rn(__fadd2_rn(psa, psb), __fadd2_rn(psc, psd));
+    l_sum += ps2.x + ps2.y;
+    // feed one bit of every packed word back into the scores so that no iteration can be hoisted or dropped
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      acc_bits ^= pw[i];
+    }
+  }
+  __syncthreads();
+  const long long t1c = clock64();
+  if (l_sum == 123.456f || acc_bits == 0x12345678u) sink[0] = 1.f;
+  if (threadIdx.x == 0) cycles[blockIdx.x] = t1c - t0c;
+}
+}  // namespace
+
+extern "C" int tdb200_selftest_softmax_exps(int variant, int warps, int iters, long long* cycles_per_cta, float* sink, void* stream) {
+  using namespace tdb;
+  if (!cycles_per_cta || !sink || warps < 1 || warps > 32 || variant < 0 || variant > 4)
+    return fail(TDB200_ERR_INVALID_ARG, "selftest_softmax_exps: variant in [0,4], warps in [1,32]");
+  if (int rc = require_sm100()) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int grid = sm_count();
+  const float sc = 1.0f / 512.0f, cb = -12582912.0f / 512.0f;
+  switch (variant) {
+    case 0: exps_probe_kernel<0><<<grid, warps * 32, 0, st>>>(iters, cycles_per_cta, sink, sc, cb); break;
+    case 1: exps_probe_kernel<1><<<grid, warps * 32, 0, st>>>(iters, cycles_per_cta, sink, sc, cb); break;
+    case 2: exps_probe_kernel<2><<<grid, warps * 32, 0, st>>>(iters, cycles_per_cta, sink, sc, cb); break;
+    case 3: exps_probe_kernel<3><<<grid, warps * 32, 0, st>>>(iters, cycles_per_cta, sink, sc, cb); break;
+    default: exps_probe_kernel<4><<<grid, warps * 32, 0, st>>>(iters, cycles_per_cta, sink, sc, cb); break;
+  }
+  return check_launch("exps_probe_kernel");
+}
