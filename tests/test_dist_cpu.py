@@ -65,6 +65,13 @@ class OraclePrimsI8(OraclePrims):
     def prepare_q(self, q):
         return None
 
+    def moments(self, k, v):
+        """Both accumulators as views of ONE buffer, like turbodiffusion_b200.SLA.core.linear_moments: SPAttention then reduces
+        them with a single collective."""
+        kv, ksum = super().moments(k, v)
+        buf = torch.cat([kv.reshape(-1), ksum.reshape(-1)]).contiguous()
+        return buf[: kv.numel()].view(kv.shape), buf[kv.numel():].view(ksum.shape)
+
     def k_partials(self, k):
         _, rows, h, d = k.shape
         pad = (-rows) % 128
