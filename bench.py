@@ -24,6 +24,7 @@ from __future__ import annotations
 
 import argparse
 import contextlib
+import datetime
 import json
 import os
 import subprocess
@@ -411,6 +412,25 @@ def extra_kernels(dev, args):
     return out
 
 
+def _leave(exit_group):
+    """End of a multi-rank run: every rank has finished its GPU work and rank 0 has printed the line.  Leave without tearing the
+    NCCL communicators down (destroy_process_group() can block after graph-captured collectives): drain the GPU, meet the other
+    ranks over the gloo group so that no process unmaps peer buffers a neighbour's last collective still reads, then _exit.  A
+    watchdog bounds the whole path: once the results are out, a rank that cannot rendezvous within 60 s leaves anyway."""
+    import threading
+    import torch
+    import torch.distributed as dist
+    sys.stdout.flush()
+    threading.Timer(60.0, lambda: os._exit(0)).start()
+    try:
+        torch.cuda.synchronize()
+        dist.barrier(group=exit_group) if exit_group is not None else dist.barrier()
+    except Exception:  # noqa: BLE001
+        pass
+    sys.stdout.flush()
+    os._exit(0)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -448,18 +468,24 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    exit_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        # host-side rendezvous for the very end of the run (see _leave): the NCCL communicators are captured into CUDA graphs and
+        # a last NCCL collective or their teardown has been seen to block, so the ranks meet over gloo instead
+        try:
+            os.environ.setdefault("GLOO_SOCKET_IFNAME", "lo")   # one node: no hostname lookup (the box's name may not resolve)
+            exit_group = dist.new_group(backend="gloo", timeout=datetime.timedelta(seconds=120))
+        except Exception as ex:  # noqa: BLE001  -- fall back to the NCCL barrier at exit (still under _leave's watchdog)
+            print(f"[bench] gloo exit group unavailable ({type(ex).__name__}: {ex}); using the NCCL barrier", file=sys.stderr)
+            exit_group = None
 
     res = run_b200(args.shape, shape, args, dev, rank, world, local_rank, args.steps, args.warmup, not args.profile, args.sp_mode)
     if args.profile:
         if rank == 0:
             print(json.dumps({"profile_run": True, "ms_per_step": res["ms_step"], "gpu_launches": res["launches"]}), flush=True)
         if world > 1:
-            torch.cuda.synchronize()
-            dist.barrier()
-            sys.stdout.flush()
-            os._exit(0)
+            _leave(exit_group)
         return
 
     extras = {}
@@ -514,12 +540,7 @@ def main():
             line["extra_configs"] = extras
         print(json.dumps(line), flush=True)
     if world > 1:
-        # NCCL communicators that were captured into a CUDA graph can block in destroy_process_group(); every rank has
-        # finished its work here, so synchronise, meet at a barrier and leave without the teardown.
-        torch.cuda.synchronize()
-        dist.barrier()
-        sys.stdout.flush()
-        os._exit(0)
+        _leave(exit_group)
 
 
 if __name__ == "__main__":
