@@ -67,10 +67,14 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region.  The sampler process is started before the warm-up
+    steps (nvidia-smi needs a few hundred ms to come up on an 8-GPU box, longer than a short timed region); every row is stamped
+    on arrival and summary() uses the rows that arrived between mark_start() and mark_end(), or - if the timed region was too
+    short to catch one - the rows since the sampler started (GPU under the same load: warm-up + timed), and says which."""
 
     def __init__(self, index: int):
         self.index, self.rows, self.proc = index, [], None
+        self.t0 = self.t1 = None
 
     def __enter__(self):
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -86,9 +90,17 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def mark_start(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def __exit__(self, *a):
+        if self.t1 is None:
+            self.t1 = time.time()
         if self.proc:
             self.proc.terminate()
             try:
@@ -97,15 +109,22 @@ class ClockSampler:
                 pass
 
     def summary(self):
-        sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
-        if not sm:
+        def ok(r):
+            return r and r[0].replace(".", "").isdigit()
+        t0 = self.t0 if self.t0 is not None else 0.0
+        t1 = self.t1 if self.t1 is not None else time.time()
+        rows, window = [r for t, r in self.rows if t0 <= t <= t1 + 0.05 and ok(r)], "timed region"
+        if not rows:
+            rows, window = [r for _, r in self.rows if ok(r)], "warm-up + timed region (timed region shorter than one sample period)"
+        if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(int(float(r[0])) for r in rows)
         reasons = []
         for i, name in enumerate(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]):
-            if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows):
+            if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in rows):
                 reasons.append(name)
-        mx = max(int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit())
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": mx, "reasons": reasons, "samples": len(sm)}
+        mx = max(int(float(r[1])) for r in rows if len(r) > 1 and r[1].replace(".", "").isdigit())
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": mx, "reasons": reasons, "samples": len(sm), "window": window}
 
 
 class KernelTimer:
@@ -254,12 +273,14 @@ def run_b200(shape_key, shape, args, dev, rank, world, local_rank, steps, warmup
     launches0 = _lib.LAUNCHES
     with ClockSampler(local_rank) as clk:
         barrier()
+        clk.mark_start()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
         for _ in range(steps):
             y = model.step(x, e0, angles, ctx)
         e.record()
         barrier()
+        clk.mark_end()
     tdo.GEMM_TIMER, sla_core.ATTN_TIMER = None, None
     launches = _lib.LAUNCHES - launches0
     eager_total = s.elapsed_time(e)
@@ -285,16 +306,18 @@ def run_b200(shape_key, shape, args, dev, rank, world, local_rank, steps, warmup
         except Exception as ex:  # noqa: BLE001
             graph, graph_note = None, f"capture failed ({type(ex).__name__}), eager timing reported"
     if graph is not None:
-        for _ in range(warmup):
-            graph.replay()
-        with ClockSampler(local_rank) as clk:
+        with ClockSampler(local_rank) as clk:      # started before the warm-up replays so that it is streaming by the timed region
+            for _ in range(warmup):
+                graph.replay()
             barrier()
+            clk.mark_start()
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s.record()
             for _ in range(steps):
                 graph.replay()
             e.record()
             barrier()
+            clk.mark_end()
         ms_step = max_over_ranks(s.elapsed_time(e) / steps)
     else:
         ms_step = ms_eager
