@@ -541,6 +541,8 @@ static int launch_v1(const void* q_op, const float* q_scale, const void* k_op, c
     return fail(TDB200_ERR_INVALID_ARG, "sla_attn_fwd: null pointer");
   if (b <= 0 || l <= 0 || lk <= 0 || h <= 0) return fail(TDB200_ERR_INVALID_ARG, "sla_attn_fwd: bad shape");
   if (d != D) return fail(TDB200_ERR_UNSUPPORTED, "sla_attn_fwd: head dim %lld (this kernel implements d=128)", (long long)d);
+  if (k_seq_major && b != 1)
+    return fail(TDB200_ERR_UNSUPPORTED, "sla_attn_fwd_kseq: batch %lld (the gathered [lk_pad, h, d] key slab is one sequence)", (long long)b);
   const int64_t mblk = cdiv64(l, BLKQ), nblk = cdiv64(lk, BLKK);
   if (topk <= 0 || topk > nblk) return fail(TDB200_ERR_INVALID_ARG, "sla_attn_fwd: topk=%lld outside [1, %lld]", (long long)topk, (long long)nblk);
   if (nblk > 65535 || h > 65535 || b > 65535) return fail(TDB200_ERR_UNSUPPORTED, "sla_attn_fwd: dimension too large");
